@@ -1,0 +1,200 @@
+// extern "C" entry points of libcytof_b200 (see include/cytof_b200.h) + the small
+// step-loop kernels (fused Adam with NaN scrub, without-replacement minibatch sampler).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cytof {
+int validate_desc(const cytof_desc* d);
+size_t workspace_bytes(const cytof_desc* d);
+int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                  const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
+                  void* workspace, size_t workspace_bytes_, cudaStream_t stream, cudaError_t* err);
+int launch_emit(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                const float* globals, float* y_out, float* eps_out, cudaStream_t stream, cudaError_t* err);
+
+// ---- Adam (torch.optim.Adam defaults as used by reference fit.py:83) + NaN scrub fit.py:24-30
+__global__ void adam_step_kernel(double* __restrict__ param, const double* __restrict__ grad,
+                                 double* __restrict__ m, double* __restrict__ v, long long n,
+                                 long long n_scrub, double grad_scale, double lr, double beta1,
+                                 double beta2, double eps, long long step_host,
+                                 long long* __restrict__ step_dev, int* __restrict__ flag) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // device-resident step counter (CUDA-graph replay): every thread reads the pre-increment
+  // value; the bump is done by a trailing 1-thread kernel (adam_bump_kernel).
+  const long long step = step_dev ? (*step_dev + 1) : step_host;
+  if (t >= n) return;
+  double g = grad[t] * grad_scale;
+  if (t < n_scrub && g != g) {
+    g = 0.0;
+    if (flag) *flag = 1;
+  }
+  const double mt = m[t] + (1.0 - beta1) * (g - m[t]);
+  const double vt = beta2 * v[t] + (1.0 - beta2) * g * g;
+  m[t] = mt;
+  v[t] = vt;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2s = sqrt(1.0 - pow(beta2, (double)step));
+  const double denom = sqrt(vt) / bc2s + eps;
+  param[t] -= (lr / bc1) * (mt / denom);
+}
+__global__ void adam_bump_kernel(long long* step_dev) { *step_dev += 1; }
+
+// ---- keyed bijection of [0, N): balanced Feistel network + cycle walking
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__global__ void sample_minibatch_kernel(long long N, long long m, unsigned long long key, int hbits,
+                                        int32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const uint32_t hmask = (1u << hbits) - 1u;
+  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  unsigned long long x = (unsigned long long)t;
+  do {
+    uint32_t L = (uint32_t)(x >> hbits) & hmask, R = (uint32_t)x & hmask;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r) ^ (k1 << (r & 7))) & hmask;
+      const uint32_t nl = R;
+      R = L ^ f;
+      L = nl;
+    }
+    x = ((unsigned long long)L << hbits) | R;
+  } while (x >= (unsigned long long)N);
+  out[t] = (int32_t)x;
+}
+__global__ void iota_kernel(long long N, int32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < N) out[t] = (int32_t)t;
+}
+
+static thread_local char g_cuda_err[256] = "";
+static void set_cuda_err(cudaError_t e) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace cytof
+
+using namespace cytof;
+
+extern "C" {
+
+int cytof_abi_version(void) { return CYTOF_ABI_VERSION; }
+
+const char* cytof_strerror(int code) {
+  switch (code) {
+    case CYTOF_OK: return "ok";
+    case CYTOF_EINVAL: return "invalid descriptor or null pointer";
+    case CYTOF_ESHAPE: return "shape outside compiled limits (I<=32, J<=64, K<=64, L<=8)";
+    case CYTOF_EWORKSPACE: return "workspace too small (see cytof_workspace_bytes)";
+    case CYTOF_ECUDA: return "CUDA error (see cytof_last_cuda_error)";
+    case CYTOF_EALIGN: return "pointer not sufficiently aligned";
+    default: return "unknown error";
+  }
+}
+const char* cytof_last_cuda_error(void) { return g_cuda_err; }
+
+int cytof_globals_layout(const cytof_desc* d, int64_t off[11]) {
+  if (!d || !off) return CYTOF_EINVAL;
+  const GlobalsLayout g = globals_layout(d->I, d->J, d->K, d->L0, d->L1);
+  const int v[11] = {g.mu0, g.mu1, g.sig, g.le0, g.le1, g.lw, g.eps, g.b, g.vm, g.vls, g.total};
+  for (int i = 0; i < 11; ++i) off[i] = v[i];
+  return CYTOF_OK;
+}
+int cytof_grad_block_layout(const cytof_desc* d, int64_t off[12]) {
+  if (!d || !off) return CYTOF_EINVAL;
+  const BlockLayout g = block_layout(d->I, d->J, d->K, d->L0, d->L1);
+  const int v[12] = {g.dmu0, g.dmu1, g.dsig, g.dle0, g.dle1, g.dlw, g.dZ, g.deps, g.dvm, g.dvls, g.dlq, g.total};
+  for (int i = 0; i < 12; ++i) off[i] = v[i];
+  return CYTOF_OK;
+}
+
+size_t cytof_workspace_bytes(const cytof_desc* d) {
+  if (validate_desc(d) != CYTOF_OK) return 0;
+  return workspace_bytes(d);
+}
+
+int cytof_elbo_fwdbwd_f32(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                          const float* globals, const uint64_t* zmask, float* grad_block,
+                          double* ll_lqy, void* workspace, size_t workspace_bytes_, void* stream) {
+  int rc = validate_desc(d);
+  if (rc != CYTOF_OK) return rc;
+  if (!globals || !zmask || !grad_block || !ll_lqy || !workspace) return CYTOF_EINVAL;
+  if (!y && d->cell_begin[d->I] > 0) return CYTOF_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(ll_lqy) & 7) || (reinterpret_cast<uintptr_t>(zmask) & 7) ||
+      (reinterpret_cast<uintptr_t>(y) & 3) || (reinterpret_cast<uintptr_t>(globals) & 3))
+    return CYTOF_EALIGN;
+  cudaError_t err = cudaSuccess;
+  rc = launch_fwdbwd(d, y, idx, eps, globals, zmask, grad_block, ll_lqy, workspace, workspace_bytes_,
+                     (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_impute_emit_f32(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                          const float* globals, float* y_out, void* stream) {
+  int rc = validate_desc(d);
+  if (rc != CYTOF_OK) return rc;
+  if (!y || !globals || !y_out) return CYTOF_EINVAL;
+  cudaError_t err = cudaSuccess;
+  rc = launch_emit(d, y, idx, eps, globals, y_out, nullptr, (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_noise_emit_f32(const cytof_desc* d, const int32_t* idx, float* eps_out, void* stream) {
+  int rc = validate_desc(d);
+  if (rc != CYTOF_OK) return rc;
+  if (!eps_out) return CYTOF_EINVAL;
+  cytof_desc dd = *d;
+  dd.noise_mode = CYTOF_NOISE_PHILOX;
+  cudaError_t err = cudaSuccess;
+  rc = launch_emit(&dd, nullptr, idx, nullptr, nullptr, nullptr, eps_out, (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_adam_step_f64(double* param, const double* grad, double* exp_avg, double* exp_avg_sq,
+                        int64_t n, int64_t n_scrub, double grad_scale, double lr, double beta1,
+                        double beta2, double eps, int64_t step_count, int64_t* step_dev,
+                        int32_t* flag, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0) return CYTOF_EINVAL;
+  if (n == 0) return CYTOF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      param, grad, exp_avg, exp_avg_sq, n, n_scrub, grad_scale, lr, beta1, beta2, eps,
+      (long long)step_count, reinterpret_cast<long long*>(step_dev), flag);
+  if (step_dev) adam_bump_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_dev));
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_cuda_err(err); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
+
+int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
+                           int32_t* idx_out, void* stream) {
+  if (!idx_out || N < 0 || m < 0 || N > 0x7fffffffLL) return CYTOF_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 0 || m == 0) return CYTOF_OK;
+  if (m >= N) {
+    iota_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(N, idx_out);
+  } else {
+    int bits = 1;
+    while ((1LL << bits) < N) ++bits;
+    int hbits = (bits + 1) / 2;
+    if (hbits < 1) hbits = 1;
+    // splitmix64 of (seed, step, sample) -> Feistel key
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(sample + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    sample_minibatch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(N, m, z, hbits, idx_out);
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_cuda_err(err); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Device helpers shared by the sm_100a kernels of cytof_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cytof_b200.h"
+
+namespace cytof {
+
+constexpr int kThreads = 256;             // 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kHalfLog2Pi = 0.9189385332046727f;  // 0.5*log(2*pi)
+constexpr float kNegBig = -1.0e30f;                   // stands in for log(0) without inf-inf NaNs
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 4-byte load that does not pollute L1 (each y row is read exactly once)
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based, no state ----
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// One standard-normal draw for (global row, marker j) of step `step` (Box-Muller on two
+// Philox words).  Independent of how cells are split over warps, CTAs or GPUs.
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t step, uint64_t grow, uint32_t j) {
+  uint32_t c[4] = {(uint32_t)grow, (uint32_t)(grow >> 32), j, step};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * kLn2 * fast_lg2(u1));
+  return r * __cosf(6.283185307179586f * u2);
+}
+
+// Offsets (in floats) of the sections of `globals` (include/cytof_b200.h).
+struct GlobalsLayout {
+  int mu0, mu1, sig, le0, le1, lw, eps, b, vm, vls, total;
+};
+__host__ __device__ inline GlobalsLayout globals_layout(int I, int J, int K, int L0, int L1) {
+  GlobalsLayout g;
+  int o = 0;
+  g.mu0 = o; o += L0;
+  g.mu1 = o; o += L1;
+  g.sig = o; o += I;
+  g.le0 = o; o += I * J * L0;
+  g.le1 = o; o += I * J * L1;
+  g.lw = o; o += I * K;
+  g.eps = o; o += I;
+  g.b = o; o += I * 3;
+  g.vm = o; o += I * J;
+  g.vls = o; o += I * J;
+  g.total = o;
+  return g;
+}
+
+// Offsets of the sections of `grad_block`.
+struct BlockLayout {
+  int dmu0, dmu1, dsig, dle0, dle1, dlw, dZ, deps, dvm, dvls, dlq, total;
+};
+__host__ __device__ inline BlockLayout block_layout(int I, int J, int K, int L0, int L1) {
+  BlockLayout g;
+  int o = 0;
+  g.dmu0 = o; o += L0;
+  g.dmu1 = o; o += L1;
+  g.dsig = o; o += I;
+  g.dle0 = o; o += I * J * L0;
+  g.dle1 = o; o += I * J * L1;
+  g.dlw = o; o += I * K;
+  g.dZ = o; o += J * K;
+  g.deps = o; o += I;
+  g.dvm = o; o += I * J;
+  g.dvls = o; o += I * J;
+  g.dlq = o; o += I * J;
+  g.total = o;
+  return g;
+}
+
+// Per-CTA partial-sum record written by the fused kernel and consumed by the finalise
+// kernel.  One CTA only ever sees cells of ONE sample, so per-sample sections need no
+// sample index here.
+struct PartialLayout {
+  int sw0, sw1, swd0, swd1, sc, gW, dZ, dvm, dvls, nm, dbl, total;
+  // sc: [0]=sum w d^2  [1]=sum fac*rho  [2]=sum fac*(1-rho)   dbl: 2 doubles (ll, lqy) as 4 floats
+};
+__host__ __device__ inline PartialLayout partial_layout(int J, int K, int L0, int L1) {
+  PartialLayout g;
+  int o = 0;
+  g.sw0 = o; o += J * L0;
+  g.sw1 = o; o += J * L1;
+  g.swd0 = o; o += L0;
+  g.swd1 = o; o += L1;
+  g.sc = o; o += 4;
+  g.gW = o; o += K;
+  g.dZ = o; o += J * K;
+  g.dvm = o; o += J;
+  g.dvls = o; o += J;
+  g.nm = o; o += J;
+  o = (o + 3) & ~3;
+  g.dbl = o; o += 4;
+  g.total = (o + 3) & ~3;
+  return g;
+}
+
+struct ElboParams {
+  const float* __restrict__ y;
+  const int32_t* __restrict__ idx;
+  const float* __restrict__ eps;
+  const float* __restrict__ globals;
+  const unsigned long long* __restrict__ zmask;
+  float* partials;
+  float* y_out;  // impute-emit mode only
+  int I, J, K, L0, L1;
+  int noise_mode;
+  float noisy_sd, scale;
+  unsigned long long seed;
+  uint32_t step;
+  int nblocks;
+  long long cell_begin[CYTOF_MAX_SAMPLES + 1];
+  long long row_base[CYTOF_MAX_SAMPLES];
+  long long row_global[CYTOF_MAX_SAMPLES];
+  float fac[CYTOF_MAX_SAMPLES];
+  int blk_begin[CYTOF_MAX_SAMPLES + 1];
+};
+
+}  // namespace cytof

@@ -1,0 +1,691 @@
+// Fused forward + backward of the per-cell part of the CyTOF ELBO for sm_100a.
+//
+// Replaces (reference paths): cytofpy/model/vae.py:17-41 (imputation + log_qy),
+// cytofpy/model/Model.py:210-278 (loglike) and the autograd backward of both.
+//
+// Mapping.  One warp owns one cell at a time and lane = marker j (J <= 32: one marker per
+// lane, the 128-byte row of y is one coalesced request; J <= 64: two markers per lane).
+// The mixture statistics that must be reduced over cells are (j,l)-indexed, so with
+// lane = j every lane keeps its own accumulators in registers for the whole kernel and
+// no per-cell cross-lane traffic is needed for them.  The Z-gated J->K sum switches the
+// warp to lane = feature k through a per-warp shared-memory row (D_j broadcast to every
+// lane), the logsumexp over K is a warp-shuffle reduction, and the responsibilities g_k go
+// back through a second shared-memory row for the backward (c1_j, dZ_jk).  A CTA only sees
+// cells of ONE sample, so all per-sample constants live in registers.
+//
+// Arithmetic is fp32 in the log2 domain (ex2/lg2 are the MUFU natives); ll is carried in
+// fp64 per warp; per-CTA partial sums are combined in a fixed order in shared memory, and
+// the finalise kernel sums the per-CTA records in fp64 in a fixed order => bitwise
+// reproducible results for a given grid.
+#include "common.cuh"
+
+namespace cytof {
+
+template <int LM0, int LM1, int JP, int KP, bool NOISY>
+__global__ void __launch_bounds__(kThreads, 1)
+elbo_fwdbwd_kernel(const ElboParams p) {
+  constexpr bool ZF = (JP == 1 && KP == 1);  // Z rows/columns held as float registers
+  constexpr int JW = JP * 32, KW = KP * 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sD = smem + warp * (JW + KW);
+  float* sG = sD + JW;
+  float* sred = smem + kWarps * (JW + KW);
+
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  int i = 0;
+  while (i + 1 < I && (int)blockIdx.x >= p.blk_begin[i + 1]) ++i;
+  const int nb = p.blk_begin[i + 1] - p.blk_begin[i];
+  const int lb = (int)blockIdx.x - p.blk_begin[i];
+  const long long cb = p.cell_begin[i];
+  const long long Bi = p.cell_begin[i + 1] - cb;
+  const long long c_lo = Bi * lb / nb, c_hi = Bi * (lb + 1) / nb;
+  const long long row_base = p.row_base[i];
+  const unsigned long long grow_base = (unsigned long long)p.row_global[i];
+
+  // ---------------- per-sample constants -> registers ----------------
+  const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
+  const float* __restrict__ G = p.globals;
+  const float sig = G[gl.sig + i];
+  const float inv_sig2 = 1.0f / (sig * sig);
+  const float h2 = 0.5f * inv_sig2 * kLog2e;
+  const float cbase = (-logf(sig) - kHalfLog2Pi) * kLog2e;
+  const float fac = p.fac[i];
+  const float b0 = G[gl.b + 3 * i], b1 = G[gl.b + 3 * i + 1], b2 = G[gl.b + 3 * i + 2];
+
+  float mu0[LM0], mu1[LM1];
+#pragma unroll
+  for (int l = 0; l < LM0; ++l) mu0[l] = l < L0 ? G[gl.mu0 + l] : 0.f;
+#pragma unroll
+  for (int l = 0; l < LM1; ++l) mu1[l] = l < L1 ? G[gl.mu1 + l] : 0.f;
+
+  bool ok[JP];
+  float okf[JP], cz0[JP][LM0], cz1[JP][LM1], vm[JP], vls[JP], sd[JP];
+  unsigned long long zrow[JP];
+#pragma unroll
+  for (int jp = 0; jp < JP; ++jp) {
+    const int j = lane + 32 * jp;
+    ok[jp] = j < J;
+    okf[jp] = ok[jp] ? 1.f : 0.f;
+    const int jj = ok[jp] ? j : 0;
+#pragma unroll
+    for (int l = 0; l < LM0; ++l)
+      cz0[jp][l] = (ok[jp] && l < L0) ? fmaf(G[gl.le0 + (i * J + jj) * L0 + (l < L0 ? l : 0)], kLog2e, cbase)
+                                      : (l == 0 ? 0.f : kNegBig);
+#pragma unroll
+    for (int l = 0; l < LM1; ++l)
+      cz1[jp][l] = (ok[jp] && l < L1) ? fmaf(G[gl.le1 + (i * J + jj) * L1 + (l < L1 ? l : 0)], kLog2e, cbase)
+                                      : (l == 0 ? 0.f : kNegBig);
+    vm[jp] = G[gl.vm + i * J + jj];
+    vls[jp] = G[gl.vls + i * J + jj];
+    sd[jp] = expf(vls[jp]);
+    const unsigned long long kmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
+    zrow[jp] = ok[jp] ? (p.zmask[jj] & kmask) : 0ull;
+  }
+  unsigned long long zcol[KP];
+  float lw2[KP];
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) {
+    const int k = lane + 32 * kp;
+    unsigned long long m = 0;
+    if (k < K)
+      for (int j = 0; j < J; ++j) m |= ((p.zmask[j] >> k) & 1ull) << j;
+    zcol[kp] = m;
+    lw2[kp] = k < K ? G[gl.lw + i * K + k] * kLog2e : kNegBig;
+  }
+  float zcf[ZF ? JW : 1], zrf[ZF ? KW : 1];
+  if constexpr (ZF) {
+#pragma unroll
+    for (int j = 0; j < JW; ++j) zcf[j] = (float)((zcol[0] >> j) & 1ull);
+#pragma unroll
+    for (int k = 0; k < KW; ++k) zrf[k] = (float)((zrow[0] >> k) & 1ull);
+  }
+  // noisy class constants (log2 domain)
+  float l1me2 = 0.f, zconst2 = 0.f, inv2s2 = 0.f, inv_s2n = 0.f;
+  if (NOISY) {
+    const float e_i = G[gl.eps + i];
+    l1me2 = log1pf(-e_i) * kLog2e;
+    zconst2 = ((float)J * (-kHalfLog2Pi - logf(p.noisy_sd)) + logf(e_i)) * kLog2e;
+    inv_s2n = 1.0f / (p.noisy_sd * p.noisy_sd);
+    inv2s2 = 0.5f * inv_s2n * kLog2e;
+  }
+
+  // ---------------- accumulators ----------------
+  float sw0[JP][LM0], sw1[JP][LM1], swd0[LM0], swd1[LM1], dZ[JP][KW], gW[KP];
+  float dvm[JP], dvls[JP], nm[JP];
+  float swdd = 0.f, sfr = 0.f, sfo = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
+  double ll2 = 0.0;
+#pragma unroll
+  for (int l = 0; l < LM0; ++l) swd0[l] = 0.f;
+#pragma unroll
+  for (int l = 0; l < LM1; ++l) swd1[l] = 0.f;
+#pragma unroll
+  for (int kp = 0; kp < KP; ++kp) gW[kp] = 0.f;
+#pragma unroll
+  for (int jp = 0; jp < JP; ++jp) {
+    dvm[jp] = dvls[jp] = nm[jp] = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM0; ++l) sw0[jp][l] = 0.f;
+#pragma unroll
+    for (int l = 0; l < LM1; ++l) sw1[jp][l] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) dZ[jp][k] = 0.f;
+  }
+
+  // ---------------- stream the cells of this CTA ----------------
+  const int32_t* __restrict__ idx = p.idx;
+  auto row_of = [&](long long c) -> long long {
+    return row_base + (idx ? (long long)__ldg(idx + cb + c) : c);
+  };
+  long long c = c_lo + warp;
+  long long row_cur = 0, row_next = 0;
+  float y_cur[JP];
+#pragma unroll
+  for (int jp = 0; jp < JP; ++jp) y_cur[jp] = 0.f;
+  if (c < c_hi) {
+    row_cur = row_of(c);
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp)
+      if (ok[jp]) y_cur[jp] = ld_stream(p.y + row_cur * J + lane + 32 * jp);
+    if (c + kWarps < c_hi) row_next = row_of(c + kWarps);
+  }
+
+  for (; c < c_hi; c += kWarps) {
+    // prefetch: y of the next cell, row index of the one after
+    float y_nxt[JP];
+    long long row_nn = 0;
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) y_nxt[jp] = 0.f;
+    if (c + kWarps < c_hi) {
+#pragma unroll
+      for (int jp = 0; jp < JP; ++jp)
+        if (ok[jp]) y_nxt[jp] = ld_stream(p.y + row_next * J + lane + 32 * jp);
+      if (c + 2 * kWarps < c_hi) row_nn = row_of(c + 2 * kWarps);
+    }
+
+    // ---- imputation of missing entries (vae.py:17-33)
+    bool miss[JP];
+    float e[JP], yv[JP];
+    bool anym = false;
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) {
+      miss[jp] = ok[jp] && (y_cur[jp] != y_cur[jp]);
+      anym |= miss[jp];
+      e[jp] = 0.f;
+      yv[jp] = ok[jp] ? y_cur[jp] : 0.f;
+    }
+    anym = __any_sync(FULL, anym);
+    if (anym) {
+#pragma unroll
+      for (int jp = 0; jp < JP; ++jp)
+        if (miss[jp]) {
+          const int j = lane + 32 * jp;
+          e[jp] = p.noise_mode == CYTOF_NOISE_EXTERNAL
+                      ? (p.eps ? __ldg(p.eps + (cb + c) * J + j) : 0.f)
+                      : philox_normal(p.seed, p.step, grow_base + (unsigned long long)(row_cur - row_base), j);
+          yv[jp] = fmaf(sd[jp], e[jp], vm[jp]);
+        }
+    }
+
+    // ---- mixture log-densities, forward (Model.py:223-233), log2 domain
+    float e0[JP][LM0], e1[JP][LM1], rS0[JP], rS1[JP], Dj[JP];
+    float a0sum = 0.f, y2sum = 0.f;
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) {
+      float M0 = 0.f, M1 = 0.f;
+#pragma unroll
+      for (int l = 0; l < LM0; ++l) {
+        const float d = yv[jp] - mu0[l];
+        e0[jp][l] = fmaf(-h2 * d, d, cz0[jp][l]);
+        M0 = l == 0 ? e0[jp][0] : fmaxf(M0, e0[jp][l]);
+      }
+#pragma unroll
+      for (int l = 0; l < LM1; ++l) {
+        const float d = yv[jp] - mu1[l];
+        e1[jp][l] = fmaf(-h2 * d, d, cz1[jp][l]);
+        M1 = l == 0 ? e1[jp][0] : fmaxf(M1, e1[jp][l]);
+      }
+      float S0 = 0.f, S1 = 0.f;
+#pragma unroll
+      for (int l = 0; l < LM0; ++l) {
+        e0[jp][l] = fast_ex2(e0[jp][l] - M0);
+        S0 += e0[jp][l];
+      }
+#pragma unroll
+      for (int l = 0; l < LM1; ++l) {
+        e1[jp][l] = fast_ex2(e1[jp][l] - M1);
+        S1 += e1[jp][l];
+      }
+      const float A0 = M0 + fast_lg2(S0), A1 = M1 + fast_lg2(S1);
+      rS0[jp] = fast_rcp(S0);
+      rS1[jp] = fast_rcp(S1);
+      Dj[jp] = okf[jp] * (A1 - A0);
+      a0sum = fmaf(okf[jp], A0, a0sum);
+      y2sum = fmaf(yv[jp], yv[jp], y2sum);
+      sD[lane + 32 * jp] = Dj[jp];
+    }
+    a0sum = warp_sum(a0sum);
+    if (NOISY) y2sum = warp_sum(y2sum);
+    __syncwarp();
+
+    // ---- Z-gated J->K sum + log W (Model.py:246-252): lane = feature k
+    float f[KP], mx = kNegBig;
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (ZF) {
+#pragma unroll
+        for (int q = 0; q < JW / 4; ++q) {
+          const float4 d4 = *reinterpret_cast<const float4*>(sD + 4 * q);
+          a[0] = fmaf(zcf[4 * q + 0], d4.x, a[0]);
+          a[1] = fmaf(zcf[4 * q + 1], d4.y, a[1]);
+          a[2] = fmaf(zcf[4 * q + 2], d4.z, a[2]);
+          a[3] = fmaf(zcf[4 * q + 3], d4.w, a[3]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < JW / 4; ++q) {
+          const float4 d4 = *reinterpret_cast<const float4*>(sD + 4 * q);
+          a[0] += ((zcol[kp] >> (4 * q + 0)) & 1ull) ? d4.x : 0.f;
+          a[1] += ((zcol[kp] >> (4 * q + 1)) & 1ull) ? d4.y : 0.f;
+          a[2] += ((zcol[kp] >> (4 * q + 2)) & 1ull) ? d4.z : 0.f;
+          a[3] += ((zcol[kp] >> (4 * q + 3)) & 1ull) ? d4.w : 0.f;
+        }
+      }
+      f[kp] = ((a[0] + a[1]) + (a[2] + a[3])) + a0sum + lw2[kp];
+      mx = fmaxf(mx, f[kp]);
+    }
+    mx = warp_max(mx);
+    float ex[KP], s = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+      ex[kp] = fast_ex2(f[kp] - mx);
+      s += ex[kp];
+    }
+    s = warp_sum(s);
+    const float lse2 = mx + fast_lg2(s);
+    const float rinv = fast_rcp(s);
+
+    // ---- noisy-cell class (Model.py:259-264)
+    float rho = 1.f, omr = 0.f, L2 = lse2;
+    if (NOISY) {
+      const float q2 = lse2 + l1me2;
+      const float z2 = fmaf(-inv2s2, y2sum, zconst2);
+      const float dd = q2 - z2;
+      const float t = fast_ex2(-fabsf(dd));
+      const float r1 = fast_rcp(1.f + t);
+      L2 = fmaxf(q2, z2) + fast_lg2(1.f + t);
+      rho = dd >= 0.f ? r1 : t * r1;
+      omr = dd >= 0.f ? t * r1 : r1;
+    }
+    ll2 += (double)L2;
+    const float fr = fac * rho;
+    sfr += fr;
+    sfo = fmaf(fac, omr, sfo);
+
+    // ---- responsibilities g_k = fac * rho * softmax_k(f)
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+      const float g = fr * rinv * ex[kp];
+      gW[kp] += g;
+      sG[lane + 32 * kp] = g;
+    }
+    __syncwarp();
+
+    // ---- backward: lane = marker j again
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) {
+      float cc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < KW / 4; ++q) {
+        const float4 g4 = *reinterpret_cast<const float4*>(sG + 4 * q);
+        if constexpr (ZF) {
+          cc[0] = fmaf(zrf[4 * q + 0], g4.x, cc[0]);
+          cc[1] = fmaf(zrf[4 * q + 1], g4.y, cc[1]);
+          cc[2] = fmaf(zrf[4 * q + 2], g4.z, cc[2]);
+          cc[3] = fmaf(zrf[4 * q + 3], g4.w, cc[3]);
+        } else {
+          cc[0] += ((zrow[jp] >> (4 * q + 0)) & 1ull) ? g4.x : 0.f;
+          cc[1] += ((zrow[jp] >> (4 * q + 1)) & 1ull) ? g4.y : 0.f;
+          cc[2] += ((zrow[jp] >> (4 * q + 2)) & 1ull) ? g4.z : 0.f;
+          cc[3] += ((zrow[jp] >> (4 * q + 3)) & 1ull) ? g4.w : 0.f;
+        }
+        dZ[jp][4 * q + 0] = fmaf(g4.x, Dj[jp], dZ[jp][4 * q + 0]);
+        dZ[jp][4 * q + 1] = fmaf(g4.y, Dj[jp], dZ[jp][4 * q + 1]);
+        dZ[jp][4 * q + 2] = fmaf(g4.z, Dj[jp], dZ[jp][4 * q + 2]);
+        dZ[jp][4 * q + 3] = fmaf(g4.w, Dj[jp], dZ[jp][4 * q + 3]);
+      }
+      const float c1 = okf[jp] * ((cc[0] + cc[1]) + (cc[2] + cc[3]));
+      const float c0 = okf[jp] * fr - c1;
+      // mixtures, backward: w_zl = c_z p_zl; statistics sum w, sum w d, sum w d^2
+      const float r0 = c0 * rS0[jp], r1 = c1 * rS1[jp];
+      float wdsum = 0.f;
+#pragma unroll
+      for (int l = 0; l < LM0; ++l) {
+        const float w = r0 * e0[jp][l];
+        const float d = yv[jp] - mu0[l];
+        const float wd = w * d;
+        sw0[jp][l] += w;
+        swd0[l] += wd;
+        swdd = fmaf(wd, d, swdd);
+        wdsum += wd;
+      }
+#pragma unroll
+      for (int l = 0; l < LM1; ++l) {
+        const float w = r1 * e1[jp][l];
+        const float d = yv[jp] - mu1[l];
+        const float wd = w * d;
+        sw1[jp][l] += w;
+        swd1[l] += wd;
+        swdd = fmaf(wd, d, swdd);
+        wdsum += wd;
+      }
+      // logistic missingness (Model.py:269-274) and d/dy chain into the imputation parameters
+      if (anym) {
+        const float u = fmaf(fmaf(b2, yv[jp], b1), yv[jp], b0);
+        const float t = fast_ex2(-fabsf(u) * kLog2e);
+        const float rr = fast_rcp(1.f + t);
+        const float ls = -(fmaxf(-u, 0.f) + kLn2 * fast_lg2(1.f + t));
+        const float sneg = (u > 0.f ? t : 1.f) * rr;  // 1 - sigmoid(u)
+        float dy = -wdsum * inv_sig2 + fac * sneg * fmaf(2.f * b2, yv[jp], b1);
+        if (NOISY) dy = fmaf(-fac * omr * inv_s2n, yv[jp], dy);
+        if (miss[jp]) {
+          lmiss_l += ls;
+          dvm[jp] += dy;
+          dvls[jp] = fmaf(dy * sd[jp], e[jp], dvls[jp]);
+          nm[jp] += 1.f;
+          lqy_l += fmaf(-0.5f * e[jp], e[jp], -vls[jp] - kHalfLog2Pi);
+        }
+      }
+    }
+    __syncwarp();  // sD / sG are rewritten by the next cell
+
+    row_cur = row_next;
+    row_next = row_nn;
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) y_cur[jp] = y_nxt[jp];
+  }
+
+  // ---------------- CTA reduction (fixed order) and partial record ----------------
+  const PartialLayout pl = partial_layout(J, K, L0, L1);
+#pragma unroll
+  for (int l = 0; l < LM0; ++l) swd0[l] = warp_sum(swd0[l]);
+#pragma unroll
+  for (int l = 0; l < LM1; ++l) swd1[l] = warp_sum(swd1[l]);
+  swdd = warp_sum(swdd);
+  lqy_l = warp_sum(lqy_l);
+  lmiss_l = warp_sum(lmiss_l);
+  double* sdbl = reinterpret_cast<double*>(sred + pl.dbl);
+  __syncthreads();
+  for (int w = 0; w < kWarps; ++w) {
+    if (warp == w) {
+      auto put = [&](int off, float v) {
+        if (w == 0) sred[off] = v; else sred[off] += v;
+      };
+#pragma unroll
+      for (int jp = 0; jp < JP; ++jp) {
+        const int j = lane + 32 * jp;
+        if (ok[jp]) {
+#pragma unroll
+          for (int l = 0; l < LM0; ++l) if (l < L0) put(pl.sw0 + l * J + j, sw0[jp][l]);
+#pragma unroll
+          for (int l = 0; l < LM1; ++l) if (l < L1) put(pl.sw1 + l * J + j, sw1[jp][l]);
+#pragma unroll
+          for (int k = 0; k < KW; ++k) if (k < K) put(pl.dZ + k * J + j, dZ[jp][k]);
+          put(pl.dvm + j, dvm[jp]);
+          put(pl.dvls + j, dvls[jp]);
+          put(pl.nm + j, nm[jp]);
+        }
+      }
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) {
+        const int k = lane + 32 * kp;
+        if (k < K) put(pl.gW + k, gW[kp]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int l = 0; l < LM0; ++l) if (l < L0) put(pl.swd0 + l, swd0[l]);
+#pragma unroll
+        for (int l = 0; l < LM1; ++l) if (l < L1) put(pl.swd1 + l, swd1[l]);
+        put(pl.sc + 0, swdd);
+        put(pl.sc + 1, sfr);
+        put(pl.sc + 2, sfo);
+        put(pl.sc + 3, 0.f);
+        const double llw = (double)fac * (ll2 * 0.6931471805599453 + (double)lmiss_l);
+        const double lqw = (double)fac * (double)p.scale * (double)lqy_l;
+        if (w == 0) { sdbl[0] = llw; sdbl[1] = lqw; } else { sdbl[0] += llw; sdbl[1] += lqw; }
+      }
+    }
+    __syncthreads();
+  }
+  float* out = p.partials + (size_t)blockIdx.x * pl.total;
+  for (int t = threadIdx.x; t < pl.total; t += kThreads) out[t] = sred[t];
+}
+
+// One thread per output of the gradient block (+ ll, log_qy): sums the per-CTA records of
+// the relevant sample(s) in fp64, fixed order, and applies the per-sample scalings.
+__global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
+                                     double* __restrict__ ll_lqy) {
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  const BlockLayout bl = block_layout(I, J, K, L0, L1);
+  const PartialLayout pl = partial_layout(J, K, L0, L1);
+  const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= bl.total + 2) return;
+  const float* __restrict__ P = p.partials;
+  const float* __restrict__ G = p.globals;
+  auto sum_sample = [&](int i, int off) -> double {
+    double a = 0.0;
+    for (int b = p.blk_begin[i]; b < p.blk_begin[i + 1]; ++b) a += (double)P[(size_t)b * pl.total + off];
+    return a;
+  };
+  if (t >= bl.total) {  // ll, log_qy
+    const int which = t - bl.total;
+    double a = 0.0;
+    for (int b = 0; b < p.nblocks; ++b)
+      a += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
+    ll_lqy[which] = a;
+    return;
+  }
+  double r = 0.0;
+  if (t < bl.dmu1) {  // dmu0[l] = sum_i (1/sig_i^2) sum w d
+    const int l = t - bl.dmu0;
+    for (int i = 0; i < I; ++i) {
+      const double s = (double)G[gl.sig + i];
+      r += sum_sample(i, pl.swd0 + l) / (s * s);
+    }
+  } else if (t < bl.dsig) {
+    const int l = t - bl.dmu1;
+    for (int i = 0; i < I; ++i) {
+      const double s = (double)G[gl.sig + i];
+      r += sum_sample(i, pl.swd1 + l) / (s * s);
+    }
+  } else if (t < bl.dle0) {  // dsig_i = sum w d^2 / sig^3 - (J sum fac rho) / sig
+    const int i = t - bl.dsig;
+    const double s = (double)G[gl.sig + i];
+    r = sum_sample(i, pl.sc + 0) / (s * s * s) - (double)J * sum_sample(i, pl.sc + 1) / s;
+  } else if (t < bl.dle1) {
+    const int q = t - bl.dle0, i = q / (J * L0), j = (q / L0) % J, l = q % L0;
+    r = sum_sample(i, pl.sw0 + l * J + j);
+  } else if (t < bl.dlw) {
+    const int q = t - bl.dle1, i = q / (J * L1), j = (q / L1) % J, l = q % L1;
+    r = sum_sample(i, pl.sw1 + l * J + j);
+  } else if (t < bl.dZ) {
+    const int q = t - bl.dlw, i = q / K, k = q % K;
+    r = sum_sample(i, pl.gW + k);
+  } else if (t < bl.deps) {  // dZ_jk = ln2 * sum g_k D2_j   (D2 in log2 units)
+    const int q = t - bl.dZ, j = q / K, k = q % K;
+    for (int i = 0; i < I; ++i) r += sum_sample(i, pl.dZ + k * J + j);
+    r *= 0.6931471805599453;
+  } else if (t < bl.dvm) {  // deps_i = -sum fac rho/(1-eps) + sum fac (1-rho)/eps
+    const int i = t - bl.deps;
+    const double e = (double)G[gl.eps + i];
+    r = -sum_sample(i, pl.sc + 1) / (1.0 - e) + sum_sample(i, pl.sc + 2) / e;
+  } else if (t < bl.dvls) {
+    const int q = t - bl.dvm, i = q / J, j = q % J;
+    r = sum_sample(i, pl.dvm + j);
+  } else if (t < bl.dlq) {
+    const int q = t - bl.dvls, i = q / J, j = q % J;
+    r = sum_sample(i, pl.dvls + j);
+  } else {  // d log_qy / d vls_ij = -fac_i * scale * #missing
+    const int q = t - bl.dlq, i = q / J, j = q % J;
+    r = -(double)p.fac[i] * (double)p.scale * sum_sample(i, pl.nm + j);
+  }
+  grad_block[t] = (float)r;
+}
+
+// y_out[C,J] = imputed minibatch (vae.py:33); eps_out[C,J] = the Philox draws.
+__global__ void impute_emit_kernel(const ElboParams p, float* __restrict__ eps_out) {
+  const long long C = p.cell_begin[p.I];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= C * p.J) return;
+  const long long c = t / p.J;
+  const int j = (int)(t % p.J);
+  int i = 0;
+  while (i + 1 < p.I && c >= p.cell_begin[i + 1]) ++i;
+  const long long lc = c - p.cell_begin[i];
+  const long long lrow = p.idx ? (long long)p.idx[c] : lc;
+  float e = 0.f;
+  if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
+    if (p.eps) e = p.eps[c * p.J + j];
+  } else {
+    e = philox_normal(p.seed, p.step, (unsigned long long)(p.row_global[i] + lrow), j);
+  }
+  if (eps_out) { eps_out[t] = e; return; }
+  const GlobalsLayout gl = globals_layout(p.I, p.J, p.K, p.L0, p.L1);
+  float v = p.y[(p.row_base[i] + lrow) * p.J + j];
+  if (v != v) v = fmaf(expf(p.globals[gl.vls + i * p.J + j]), e, p.globals[gl.vm + i * p.J + j]);
+  p.y_out[t] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+using KernelFn = void (*)(const ElboParams);
+
+struct Variant {
+  int lm0, lm1, jp, kp;
+  KernelFn fn[2];  // [noisy]
+};
+#define CYTOF_VARIANT(a, b, jp, kp) \
+  { a, b, jp, kp, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true> } }
+// ordered by cost: the first variant that fits is used; (8,8) is the padded fallback
+static const Variant kVariants[] = {
+    CYTOF_VARIANT(3, 3, 1, 1), CYTOF_VARIANT(4, 3, 1, 1), CYTOF_VARIANT(5, 3, 1, 1),
+    CYTOF_VARIANT(5, 5, 1, 1), CYTOF_VARIANT(8, 8, 1, 1),
+    CYTOF_VARIANT(3, 3, 2, 2), CYTOF_VARIANT(5, 5, 2, 2), CYTOF_VARIANT(8, 8, 2, 2),
+};
+
+static const Variant* pick_variant(int J, int K, int L0, int L1) {
+  const int jp = J <= 32 ? 1 : 2, kp = K <= 32 ? 1 : 2;
+  const int need = jp > kp ? jp : kp;
+  for (const Variant& v : kVariants)
+    if (v.jp == need && v.kp == need && v.lm0 >= L0 && v.lm1 >= L1) return &v;
+  return nullptr;
+}
+
+static size_t fused_smem_bytes(const Variant* v, int J, int K, int L0, int L1) {
+  const PartialLayout pl = partial_layout(J, K, L0, L1);
+  return sizeof(float) * (size_t)(kWarps * (v->jp * 32 + v->kp * 32) + pl.total);
+}
+
+static int g_sm_count[64] = {0};
+static int device_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (g_sm_count[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sm_count[dev] = n;
+  }
+  return g_sm_count[dev];
+}
+
+constexpr int kMaxCtasPerSm = 4;   // upper bound used to size the workspace
+constexpr int kMinCellsPerWarp = 4;
+
+int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAMPLES; }
+
+// resident CTAs per SM of one kernel variant (cached; immutable per device + binary)
+static int g_occ[64][16][2] = {};
+static int variant_occupancy(const Variant* v, int noisy, size_t smem) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+  const int vi = (int)(v - kVariants);
+  if (g_occ[dev][vi][noisy] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn[noisy], kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    if (n > kMaxCtasPerSm) n = kMaxCtasPerSm;
+    g_occ[dev][vi][noisy] = n;
+  }
+  return g_occ[dev][vi][noisy];
+}
+
+int validate_desc(const cytof_desc* d) {
+  if (!d) return CYTOF_EINVAL;
+  if (d->I < 1 || d->I > CYTOF_MAX_SAMPLES || d->J < 1 || d->J > CYTOF_MAX_J || d->K < 1 ||
+      d->K > CYTOF_MAX_K || d->L0 < 1 || d->L0 > CYTOF_MAX_L || d->L1 < 1 || d->L1 > CYTOF_MAX_L)
+    return CYTOF_ESHAPE;
+  if (d->cell_begin[0] != 0) return CYTOF_EINVAL;
+  for (int i = 0; i < d->I; ++i)
+    if (d->cell_begin[i + 1] < d->cell_begin[i]) return CYTOF_EINVAL;
+  if (d->noise_mode != CYTOF_NOISE_EXTERNAL && d->noise_mode != CYTOF_NOISE_PHILOX) return CYTOF_EINVAL;
+  if (!pick_variant(d->J, d->K, d->L0, d->L1)) return CYTOF_ESHAPE;
+  return CYTOF_OK;
+}
+
+void fill_params(const cytof_desc* d, ElboParams* p) {
+  p->I = d->I; p->J = d->J; p->K = d->K; p->L0 = d->L0; p->L1 = d->L1;
+  p->noise_mode = d->noise_mode;
+  p->noisy_sd = d->noisy_sd;
+  p->scale = d->scale;
+  p->seed = d->seed;
+  p->step = (uint32_t)d->step;
+  for (int i = 0; i <= d->I; ++i) p->cell_begin[i] = d->cell_begin[i];
+  for (int i = 0; i < d->I; ++i) {
+    p->row_base[i] = d->row_base[i];
+    p->row_global[i] = d->row_global[i];
+    p->fac[i] = (float)d->fac[i];
+  }
+}
+
+// Splits the grid over samples proportionally to their cell counts (>= 1 CTA per non-empty
+// sample) so that a CTA never mixes samples.
+static int plan_grid(const cytof_desc* d, ElboParams* p, int occ) {
+  const long long C = d->cell_begin[d->I];
+  const int cap = device_sm_count() * occ;
+  long long want = (C + (long long)kWarps * kMinCellsPerWarp - 1) / ((long long)kWarps * kMinCellsPerWarp);
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  int b = 0;
+  for (int i = 0; i < d->I; ++i) {
+    p->blk_begin[i] = b;
+    const long long Bi = d->cell_begin[i + 1] - d->cell_begin[i];
+    if (Bi > 0) {
+      long long n = (want * Bi + C / 2) / (C > 0 ? C : 1);
+      if (n < 1) n = 1;
+      if (n > Bi) n = Bi;
+      b += (int)n;
+    }
+  }
+  p->blk_begin[d->I] = b;
+  p->nblocks = b;
+  return b;
+}
+
+size_t workspace_bytes(const cytof_desc* d) {
+  const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
+  return sizeof(float) * (size_t)pl.total * (size_t)max_grid_blocks() + 256;
+}
+
+int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                  const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
+                  void* workspace, size_t workspace_bytes_, cudaStream_t stream, cudaError_t* err) {
+  const Variant* v = pick_variant(d->J, d->K, d->L0, d->L1);
+  ElboParams p;
+  fill_params(d, &p);
+  p.y = y; p.idx = idx; p.eps = eps; p.globals = globals;
+  p.zmask = reinterpret_cast<const unsigned long long*>(zmask);
+  p.y_out = nullptr;
+  uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15;
+  p.partials = reinterpret_cast<float*>(wp);
+  const size_t smem = fused_smem_bytes(v, d->J, d->K, d->L0, d->L1);
+  const int nblocks = plan_grid(d, &p, variant_occupancy(v, d->model_noisy ? 1 : 0, smem));
+  const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
+  const size_t need = sizeof(float) * (size_t)pl.total * (size_t)nblocks + (wp - reinterpret_cast<uintptr_t>(workspace));
+  if (need > workspace_bytes_) return CYTOF_EWORKSPACE;
+  const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
+  if (nblocks > 0) {
+    KernelFn fn = v->fn[d->model_noisy ? 1 : 0];
+    if (smem > 48 * 1024) {
+      *err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (*err != cudaSuccess) return CYTOF_ECUDA;
+    }
+    fn<<<nblocks, kThreads, smem, stream>>>(p);
+    *err = cudaGetLastError();
+    if (*err != cudaSuccess) return CYTOF_ECUDA;
+  }
+  const int nout = bl.total + 2;
+  elbo_finalize_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(p, grad_block, ll_lqy);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
+}
+
+int launch_emit(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                const float* globals, float* y_out, float* eps_out, cudaStream_t stream, cudaError_t* err) {
+  ElboParams p;
+  fill_params(d, &p);
+  p.y = y; p.idx = idx; p.eps = eps; p.globals = globals; p.zmask = nullptr; p.partials = nullptr;
+  p.y_out = y_out;
+  p.nblocks = 0;
+  const long long n = d->cell_begin[d->I] * (long long)d->J;
+  if (n > 0) {
+    impute_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, eps_out);
+    *err = cudaGetLastError();
+    if (*err != cudaSuccess) return CYTOF_ECUDA;
+  }
+  return CYTOF_OK;
+}
+
+}  // namespace cytof

@@ -1,0 +1,126 @@
+"""Step loop: drop-in for reference cytofpy/model/fit.py (`update` :32-48,
+`fit` :50-147, `check_nan_in_grad` :12-30)."""
+import copy
+import datetime
+import sys
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .core import Model
+from .priors import default_priors
+
+import ctypes as C
+
+
+def check_nan_in_grad(mp, key, fixed_grad, i=None):
+    """reference fit.py:12-30 for the ModelParam blocks: NaN gradient entries -> 0, flag set."""
+    vp = mp[key].vp
+    if vp.grad is None:
+        return
+    bad = torch.isnan(vp.grad)
+    if bool(bad.any()):
+        print("WARNING: Setting a nan gradient to zero in {}!".format(key))
+        vp.grad[bad] = 0.0
+        fixed_grad[0] = True
+
+
+def update(opt, mod, idx):
+    """One optimisation step (reference fit.py:32-48).  Works with any torch optimizer over
+    mod.parameters(); the NaN scrub covers the global blocks only, as in the reference."""
+    elbo, ll, lp, lq = mod(idx)
+    loss = -elbo / mod.Nsum
+    opt.zero_grad()
+    loss.backward()
+    fixed_grad = [False]
+    with torch.no_grad():
+        grads = [mod.mp[key].vp.grad for key in mod.mp if mod.mp[key].vp.grad is not None]
+        # one device sync for all blocks instead of one per block
+        if grads and bool(torch.stack([torch.isnan(g).any() for g in grads]).any()):
+            for key in mod.mp:
+                check_nan_in_grad(mod.mp, key, fixed_grad)
+    opt.step()
+    return elbo, fixed_grad[0], ll, lp, lq
+
+
+def device_minibatch(mod, minibatch_size, step, seed):
+    """Without-replacement minibatch drawn ON the device (cytof_sample_minibatch): replaces the
+    host-side np.random.choice(N_i, mb, replace=False) of reference fit.py:96-102.  Returns a
+    list of int32 device tensors / `range` objects for full batches."""
+    lib = _lib.load()
+    out = []
+    stream = torch.cuda.current_stream(mod.device).cuda_stream
+    for i, n in enumerate(mod.N_local):
+        if minibatch_size >= n:
+            out.append(range(n))
+            continue
+        t = torch.empty(minibatch_size, dtype=torch.int32, device=mod.device)
+        with torch.cuda.device(mod.device):
+            _lib.check(lib.cytof_sample_minibatch(n, minibatch_size, seed, step, i,
+                                                  C.c_void_p(t.data_ptr()), C.c_void_p(stream)))
+        out.append(t)
+    return out
+
+
+def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=10, seed=1,
+        y_mean_init=-3.0, y_sd_init=0.1, trace_every=None, eps_conv=1e-6, tau=0.1,
+        backup_every=10, y_quantiles=[0, 35, 70], p_bounds=[.05, .8, .05], scale=1,
+        use_stick_break=True, model_noisy=True, init_mp=None, verbose=1, flush=True,
+        K=30, L=None, device=None, sampler='device', noise='philox'):
+    """reference fit.py:50-147, same arguments and the same returned dict keys
+    ('elbo', 'trace', 'mp', 'tau', 'vae', 'use_stick_break', 'y', 'priors', 'model_noisy').
+
+    Extras: K / L (used when priors is None — the reference's `priors=None` branch raises
+    NameError, fit.py:68-70), device, sampler ('device' = on-GPU keyed permutation,
+    'numpy' = the reference's np.random.choice stream), noise ('philox' | 'external')."""
+    print('scale: {}'.format(scale))
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    if trace_every is None:
+        trace_every = int(max_iter / 50) if max_iter >= 50 else 1
+    m = [torch.isnan(yi) for yi in y]
+    if priors is None:
+        priors = default_priors(y, K=K, L=L, y_quantiles=y_quantiles, p_bounds=p_bounds)
+    model = Model(y=y, m=m, priors=priors, tau=tau, verbose=verbose, use_stick_break=use_stick_break,
+                  model_noisy=model_noisy, y_mean_init=y_mean_init, y_sd_init=y_sd_init, scale=scale,
+                  device=device, noise=noise, seed=seed)
+    if init_mp is not None:
+        # warm start that actually trains the given state (the reference swaps `model.mp` after
+        # the optimizer captured the old tensors, fit.py:76-83, so its resume is a no-op)
+        with torch.no_grad():
+            for key in model.mp:
+                model.mp[key].vp.copy_(init_mp[key].vp.to(model.device))
+    if verbose >= 1.1:
+        print('state_dict:')
+        print(model.state_dict())
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    best_mp = copy.deepcopy(model.mp)
+    best_vae = copy.deepcopy(model.y_vae)
+    elbo_hist, trace = [], []
+    for t in range(max_iter + 1):
+        if sampler == 'numpy':
+            idx = [np.arange(n) if minibatch_size >= n else
+                   np.random.choice(n, minibatch_size, replace=False) for n in model.N_local]
+        else:
+            idx = device_minibatch(model, minibatch_size, t, seed)
+        elbo, fixed_grad, ll, lp, lq = update(optimizer, model, idx)
+        elbo_hist.append(elbo.item())
+        elbo_good = not fixed_grad
+        if t % print_freq == 0:
+            print('{} | {}/{} | elbo: {:.3f} | ll: {:.3f} | lp: {:.3f} | lq: {:.3f}'.format(
+                datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"), t, max_iter,
+                elbo_hist[-1] / model.Nsum, ll / model.Nsum, lp / model.Nsum, lq / model.Nsum))
+        if backup_every > 0 and t % backup_every == 0 and elbo_good:
+            best_mp = copy.deepcopy(model.mp)
+            best_vae = model.y_vae
+        if trace_every > 0 and t % trace_every == 0 and elbo_good:
+            trace.append({key: copy.deepcopy(model.mp[key]) for key in model.mp})
+        if t > 10 and abs(elbo_hist[-1] / elbo_hist[-2] - 1) < eps_conv:
+            print('Convergence suspected! Ending optimizer early.')
+            break
+        if flush:
+            sys.stdout.flush()
+    return {'elbo': elbo_hist, 'trace': trace, 'mp': best_mp, 'tau': tau, 'vae': best_vae,
+            'use_stick_break': use_stick_break, 'y': y, 'priors': str(model.priors),
+            'model_noisy': model_noisy}

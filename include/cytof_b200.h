@@ -1,0 +1,130 @@
+/* cytof_b200.h — C ABI of the B200-native CyTOF ELBO hot path.
+ *
+ * The reference (luiarthur/CytofPy) is pure Python and has NO FFI seam: its
+ * hot path is Python methods of cytofpy.model.Model.  This header is therefore
+ * a new boundary placed *behind* those methods; each entry point names the
+ * reference code it replaces (paths relative to the reference root):
+ *
+ *   cytof_elbo_fwdbwd_f32   cytofpy/model/vae.py:17-41   (reparameterised imputation, log_qy)
+ *                           cytofpy/model/Model.py:210-278 (loglike: mixtures, Z-gated J->K sum,
+ *                               logsumexp over K, noisy-cell class, logistic missingness)
+ *                           + the autograd backward of both that fit.py:36 triggers
+ *   cytof_impute_emit_f32   cytofpy/model/vae.py:17-33   (materialise imputed y for
+ *                               Model.sample_params, Model.py:332-337)
+ *   cytof_noise_emit_f32    the Normal.rsample draw of vae.py:33 (test hook for Philox mode)
+ *   cytof_adam_step_f64     torch.optim.Adam as used by fit.py:83 + NaN scrub fit.py:12-30,44-45
+ *   cytof_sample_minibatch  np.random.choice(N_i, mb, replace=False), fit.py:96-102
+ *
+ * Conventions (all entry points):
+ *   - every data pointer is a DEVICE pointer owned by the caller; the library
+ *     never allocates, frees or synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - returns 0 on success or a negative CYTOF_E* code (never throws/exits);
+ *     cytof_strerror() maps codes to text;
+ *   - no global mutable state except a per-device cache of immutable device
+ *     attributes; re-entrant across streams/devices with distinct workspaces.
+ */
+#ifndef CYTOF_B200_H
+#define CYTOF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYTOF_ABI_VERSION 1
+#define CYTOF_MAX_SAMPLES 32 /* I */
+#define CYTOF_MAX_J 64       /* markers  */
+#define CYTOF_MAX_K 64       /* features */
+#define CYTOF_MAX_L 8        /* mixture components per z */
+
+#define CYTOF_OK 0
+#define CYTOF_EINVAL (-1)     /* bad descriptor / null pointer */
+#define CYTOF_ESHAPE (-2)     /* sizes outside the compiled limits */
+#define CYTOF_EWORKSPACE (-3) /* workspace too small */
+#define CYTOF_ECUDA (-4)      /* CUDA launch error (see cytof_last_cuda_error) */
+#define CYTOF_EALIGN (-5)     /* pointer not aligned as required */
+
+#define CYTOF_NOISE_EXTERNAL 0 /* eps[C,J] supplied (parity mode; only missing entries are read) */
+#define CYTOF_NOISE_PHILOX 1   /* in-kernel Philox4x32-10 keyed by (seed, step, global row, marker) */
+
+/* One ELBO evaluation ("step") over C = sum_i B_i cells.
+ * The step's cell list is sample-major: cells [cell_begin[i], cell_begin[i+1]) belong to sample i.
+ * Cell c of sample i reads row  row_base[i] + (idx ? idx[c] : c - cell_begin[i])  of y. */
+typedef struct cytof_desc {
+  int32_t I, J, K, L0, L1;
+  int32_t model_noisy; /* Model.py:259-266 on/off */
+  int32_t noise_mode;  /* CYTOF_NOISE_* */
+  int32_t reserved0;
+  float noisy_sd; /* sqrt(priors['noisy_var']), Model.py:148 */
+  float scale;    /* vae.py:41 */
+  uint64_t seed;  /* Philox key   */
+  uint64_t step;  /* Philox counter word (fit iteration) */
+  int64_t cell_begin[CYTOF_MAX_SAMPLES + 1];
+  int64_t row_base[CYTOF_MAX_SAMPLES];   /* first row of sample i inside y */
+  int64_t row_global[CYTOF_MAX_SAMPLES]; /* global id of that row (rank offset; Philox counter) */
+  double fac[CYTOF_MAX_SAMPLES];         /* N_i / B_i with GLOBAL counts, Model.py:257 */
+} cytof_desc;
+
+/* `globals` (float, device): the transformed global sample of this step, packed as
+ *   mu0[L0] | mu1[L1] | sig[I] | logeta0[I,J,L0] | logeta1[I,J,L1] | logW[I,K] |
+ *   eps[I] | b[I,3] | vm[I,J] | vls[I,J]
+ * (mu0 = -cumsum(delta0), mu1 = cumsum(delta1), sig = sqrt(sig2): Model.py:212,223,227;
+ *  eps ignored when !model_noisy; b = missingness coefficients b0,b1,b2: Model.py:139-141;
+ *  vm, vls = imputation mean / log sd: vae.py:12-13).
+ * cytof_globals_layout writes the 10 section offsets (+ total in off[10]). */
+int cytof_globals_layout(const cytof_desc* d, int64_t off[11]);
+
+/* `grad_block` (float, device, output): d ll / d(each globals entry) plus d log_qy / d vls:
+ *   dmu0[L0] | dmu1[L1] | dsig[I] | dlogeta0[I,J,L0] | dlogeta1[I,J,L1] | dlogW[I,K] |
+ *   dZ[J,K] | deps[I] | dvm[I,J] | dvls[I,J] | dlqy_dvls[I,J]
+ * cytof_grad_block_layout writes the 11 section offsets (+ total in off[11]). */
+int cytof_grad_block_layout(const cytof_desc* d, int64_t off[12]);
+
+size_t cytof_workspace_bytes(const cytof_desc* d);
+
+/* Fused forward + backward of the per-cell part of the ELBO.
+ *   y        [rows, J] row-major fp32, NaN = missing (fit.py:66)
+ *   idx      [C] int32 sample-local row indices, or NULL for "all rows in order"
+ *   eps      [C, J] fp32 standard-normal draws (CYTOF_NOISE_EXTERNAL) or NULL (Philox)
+ *   zmask    [J] uint64, bit k of word j = 1[v_k > H_jk]  (thresholded in fp64 by the caller)
+ *   ll_lqy   [2] double: ll (Model.py:276 summed over i) and log_qy (vae.py:41 summed over i)
+ * Launches: 1 fused kernel + 1 finalise kernel. */
+int cytof_elbo_fwdbwd_f32(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                          const float* globals, const uint64_t* zmask, float* grad_block,
+                          double* ll_lqy, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Writes the imputed minibatch y_out[C, J] (vae.py:33) for the same descriptor/noise. */
+int cytof_impute_emit_f32(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                          const float* globals, float* y_out, void* stream);
+
+/* Writes the standard-normal draws eps_out[C, J] that CYTOF_NOISE_PHILOX uses (test hook). */
+int cytof_noise_emit_f32(const cytof_desc* d, const int32_t* idx, float* eps_out, void* stream);
+
+/* Adam over a flat fp64 buffer.  n_scrub leading entries get NaN gradients replaced by 0
+ * (fit.py:24-30 scrubs the 10 global blocks but not the imputation parameters); *flag (int32,
+ * device, may be NULL) is set to 1 if anything was scrubbed.  grad_scale multiplies the raw
+ * gradient first (fit.py:34: loss = -elbo / Nsum).  step_count is the 1-based Adam step; if
+ * step_dev (int64, device) is non-NULL the step is *step_dev + 1 instead and the counter is
+ * incremented on the stream, so the call can be captured once in a CUDA graph and replayed. */
+int cytof_adam_step_f64(double* param, const double* grad, double* exp_avg, double* exp_avg_sq,
+                        int64_t n, int64_t n_scrub, double grad_scale, double lr, double beta1,
+                        double beta2, double eps, int64_t step_count, int64_t* step_dev,
+                        int32_t* flag, void* stream);
+
+/* Without-replacement minibatch: writes m distinct int32 indices in [0, N) to idx_out — the
+ * first m values of a keyed pseudo-random bijection of [0, N) (cycle-walking Feistel network,
+ * key = (seed, step, sample)), O(m) work and no scratch.  m >= N writes 0..N-1 (fit.py:98-99). */
+int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
+                           int32_t* idx_out, void* stream);
+
+const char* cytof_strerror(int code);
+const char* cytof_last_cuda_error(void);
+int cytof_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYTOF_B200_H */
