@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the ELBO forward+backward hot path (metric of BASELINE.json:
+"ELBO fwd+bwd cells/sec (J=32,K=30,L=5) at 1/2/4/8 B200; % of HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4]
+
+A "step" is one full `update` of the reference (fit.py:32-48): draw the global
+sample, transforms, per-cell ELBO forward+backward over ONE batch (the fused
+CUDA kernel), log prior, entropy, backward to every variational parameter, NaN
+scrub and the Adam step.  The default workload is BASELINE.json configs[3]
+("cfg4": full batch, I=8, J=32, K=30, L=5/5) — the configuration the metric
+string names — with 1,000,000 cells PER GPU (weak scaling: rank r holds rows
+[r*125000, (r+1)*125000) of each of the 8 samples; one all-reduce of the
+~4.3k-float gradient block per step).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: I, cells per sample (per GPU), J, K, L0, L1, minibatch (None = full batch), NaN rate, fit kwargs
+    'cfg1': dict(I=3, n=2000, J=32, K=5, L0=3, L1=3, mb=None, nan=0.0, kw={}),
+    'cfg2': dict(I=3, n=40000, J=32, K=30, L0=5, L1=3, mb=2000, nan=0.0, kw={}),
+    'cfg3': dict(I=3, n=40000, J=32, K=30, L0=5, L1=3, mb=2000, nan=0.3,
+                 kw=dict(use_stick_break=False, scale=.1, tau=0.001)),
+    'cfg4': dict(I=8, n=125000, J=32, K=30, L0=5, L1=5, mb=None, nan=0.0, kw={}),
+    'cfg5': dict(I=8, n=1250000, J=40, K=50, L0=8, L1=8, mb=None, nan=0.0, kw={}),
+}
+METRIC = 'ELBO fwd+bwd cells/sec (J=32,K=30,L=5)'
+UNIT = 'cells/s'
+L2_FLUSH_BYTES = 512 << 20
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def make_data(w, seed):
+    import cytofpy_b200 as cy
+    s = cy.util.synth_cytof([w['n']] * w['I'], w['J'], [100.] * 5, w['L0'], w['L1'], seed=seed)
+    if w['nan'] > 0:
+        beta = cy.model.solve_beta([-5., -3.5, -2.], [.05, .8, .05]).numpy()
+        cy.util.inject_missing(s['y'], beta, rate=w['nan'], seed=seed + 1)
+    return s['y']
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons during the timed region (NVML)"""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+               0x4: 'sw_power_cap', 0x80: 'hw_power_brake', 0x2: 'applications_clocks_setting'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report it, do not fake numbers
+            self.reasons.add('nvml_unavailable:%s' % type(e).__name__)
+
+    def summary(self):
+        return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm)}
+
+
+def time_cpu_port(w, steps, warmup, cells_per_sample, threads=None):
+    """The oracle port of the reference `update` (fp64 torch + autograd + Adam) on host cores,
+    on a bounded sample of the workload: same I/J/K/L, `cells_per_sample` cells per sample."""
+    from oracle import elbo_port as port
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    ws = dict(w, n=cells_per_sample)
+    y = [torch.tensor(a, dtype=torch.float64) for a in make_data(ws, seed=0)]
+    kw = w['kw']
+    cfg = port.make_cfg(y, w['K'], w['L0'], w['L1'], tau=kw.get('tau', .1),
+                        use_stick_break=kw.get('use_stick_break', True), scale=kw.get('scale', 1.0))
+    st = port.init_state(w['I'], w['J'], w['K'], w['L0'], w['L1'], use_stick_break=cfg['use_stick_break'])
+    opt = torch.optim.Adam(port.state_parameters(st), lr=1e-2)
+    mb = w['mb'] if w['mb'] and w['mb'] < cells_per_sample else None
+    rng = np.random.RandomState(0)
+    times, cells = [], 0
+    for t in range(warmup + steps):
+        t0 = time.perf_counter()
+        idx = [np.arange(cells_per_sample) if mb is None else rng.choice(cells_per_sample, mb, replace=False)
+               for _ in range(w['I'])]
+        port.update_port(opt, st, y, idx, port.draw_noise(cfg, idx), cfg)
+        if t >= warmup:
+            times.append(time.perf_counter() - t0)
+            cells = sum(len(ix) for ix in idx)
+    med = statistics.median(times)
+    return cells / med, torch.get_num_threads(), cells, med
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    per = min(w['n'], 4000 if w['mb'] is None else w['n'])
+    v, cores, cells, med = time_cpu_port(w, args.steps, args.warmup, per)
+    sample = 'oracle port of reference update (fp64 torch CPU, autograd, Adam) on %d cells/step ' \
+             '(%d samples x %d%s) at the workload J/K/L' % (cells, w['I'], per,
+                                                           '' if w['mb'] is None else ', minibatch %d' % w['mb'])
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'I': w['I'], 'J': w['J'], 'K': w['K'], 'L': [w['L0'], w['L1']]},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import cytofpy_b200 as cy
+    from cytofpy_b200.model.engine import Batch
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+        group = dist.group.WORLD
+    I, n, J = w['I'], w['n'], w['J']
+    y_np = make_data(w, seed=1000 + rank)                      # this rank's rows
+    y = [torch.from_numpy(a) for a in y_np]
+    N_global = [n * world] * I
+    pri_y = [t[:2000].double() for t in y]
+    priors = cy.model.default_priors(pri_y, K=w['K'], L=[w['L0'], w['L1']], y_bounds=[-5., -3.5, -2.])
+    priors['N'] = N_global
+    torch.manual_seed(1)
+    model = cy.model.Model(y=y, priors=priors, verbose=-1, device=dev, noise='philox', seed=1,
+                           N_global=N_global, row_global=[rank * n] * I, dist_group=group, **w['kw'])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    mb = w['mb']
+
+    def draw_idx(t):
+        return [range(n)] * I if mb is None else cy.model.device_minibatch(model, mb, t, 1)
+
+    cells_step = I * (n if mb is None else mb)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    eng = model.engine
+
+    # ---- device-resident throughput: K timed steps, L2 flushed between them
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    for t in range(args.warmup):
+        cy.model.update(opt, model, draw_idx(t))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = eng.launches
+    for t in range(args.steps):
+        flush.fill_(t & 0xff)                                   # evict y from the 126 MB L2
+        ev[t][0].record()
+        cy.model.update(opt, model, draw_idx(args.warmup + t))
+        ev[t][1].record()
+    barrier()
+    sampler.stop_flag = True
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    launches = eng.launches - launches0
+
+    # ---- dominant kernel alone (CUDA events on the launching stream, L2 flushed)
+    model._step += 1
+    with torch.no_grad():
+        reals = model._sample_globals()
+        kin = model._kernel_inputs(model.transform(reals))
+        g32 = torch.cat([t.reshape(-1) for t in kin[:6]] + [kin[7].reshape(-1), eng.b_dev.reshape(-1),
+                                                             kin[8].reshape(-1), kin[9].reshape(-1)]).float()
+        bits = (kin[6] > 0.5).to(torch.int64)
+        zmask = (bits << torch.arange(w['K'], device=dev, dtype=torch.int64)[None, :]).sum(1).contiguous()
+    counts, idx_dev = eng.make_idx(draw_idx(0))
+    kb = Batch(counts, idx_dev, None, step=1)
+    kev = []
+    for t in range(3 + 10):
+        flush.fill_(t & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.fwdbwd(kb, g32, zmask, None if group is None else [c * world for c in counts])
+        b.record()
+        kev.append((a, b))
+    torch.cuda.synchronize(dev)
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev[3:])
+    bytes_cell = 4 * J + (4 if idx_dev is not None else 0)
+    achieved = cells_step * bytes_cell / (k_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- end to end through the public API with HOST buffers: every step copies the step's
+    # input rows from pinned host memory to the device and reads the ELBO back
+    y_pin = torch.cat(y, 0).pin_memory()
+    h2d = y_pin.numel() * 4 if mb is None else cells_step * (4 * J + 4)
+    e_ev = []
+    for t in range(2 + max(3, args.steps // 2)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        if mb is None:
+            eng.y_dev.copy_(y_pin, non_blocking=True)
+            idx = draw_idx(t)
+        else:   # minibatch: gather the step's rows on the host, ship rows + indices
+            rows = [np.random.choice(n, mb, replace=False) for _ in range(I)]
+            sel = torch.cat([torch.from_numpy(r + i * n) for i, r in enumerate(rows)])
+            stage = y_pin[sel].pin_memory()
+            eng.y_dev[:stage.shape[0]].copy_(stage, non_blocking=True)
+            idx = [torch.arange(i * mb, (i + 1) * mb, dtype=torch.int32) - i * n for i in range(I)]
+            idx = [ix.to(dev) for ix in idx]
+        elbo, *_ = cy.model.update(opt, model, idx)
+        _ = elbo.item()
+        b.record()
+        e_ev.append((a, b))
+    barrier()
+    e2e_ms = statistics.mean(a.elapsed_time(b) for a, b in e_ev[2:])
+    if mb is not None:   # restore the resident matrix
+        eng.y_dev.copy_(y_pin)
+
+    times = torch.tensor([step_ms, k_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    step_ms, k_ms_max, e2e_ms = times.tolist()
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            per = min(n, 4000 if mb is None else n)
+            v, cores, cells, med = time_cpu_port(w, 3, 1, per)
+            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                   'sample': 'oracle port of reference update (fp64 torch CPU) on %d cells/step at the '
+                             'workload J/K/L, median of 3 steps' % cells}
+        out = {
+            'metric': METRIC, 'value': cells_step * world / (step_ms * 1e-3), 'unit': UNIT,
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': args.workload, 'I': I, 'cells_per_gpu': I * n, 'cells_per_step_per_gpu': cells_step,
+                       'J': J, 'K': w['K'], 'L': [w['L0'], w['L1']], 'minibatch': mb, 'nan_rate': w['nan'],
+                       'parallelism': 'cells sharded x%d, all-reduce of gradient block' % world,
+                       'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox'},
+            'e2e': {'value': cells_step * world / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_kernel (+finalize)', 'achieved': achieved,
+                         'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak_source': peak_src, 'bytes_per_cell': bytes_cell, 'kernel_ms': k_ms,
+                         'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -56,7 +56,7 @@ class _CellELBO(torch.autograd.Function):
 class Model(torch.nn.Module):
     def __init__(self, y, priors, m=None, y_mean_init=-3.0, y_sd_init=0.1, tau=0.1, verbose=1,
                  use_stick_break=True, model_noisy=True, scale=1, device=None, noise='philox',
-                 seed=0, N_global=None, row_global=None, dist_group=None):
+                 seed=0, N_global=None, row_global=None, dist_group=None, _engine_factory=None):
         """Arguments up to `scale` are the reference's (Model.py:115-116).  Extra, all optional:
         device (default cuda:current), noise ('philox' in-kernel draws | 'external' torch
         draws, used by the parity tests), seed (Philox key), and for cell-sharded multi-GPU
@@ -121,8 +121,9 @@ class Model(torch.nn.Module):
             y_eff.append(t)
         b = torch.stack([torch.as_tensor(self.b0, dtype=F64), torch.as_tensor(self.b1, dtype=F64),
                          torch.as_tensor(self.b2, dtype=F64)], 1)
-        self.engine = CellEngine(y_eff, dev, K, L[0], L[1], model_noisy, float(self.noisy_sd),
-                                 float(scale), b, N_global=N_global, row_global=row_global, seed=seed)
+        make = CellEngine if _engine_factory is None else _engine_factory   # tests inject a stub
+        self.engine = make(y_eff, dev, K, L[0], L[1], model_noisy, float(self.noisy_sd),
+                           float(scale), b, N_global=N_global, row_global=row_global, seed=seed)
         self.N_local = self.engine.N_local
 
     # ------------------------------------------------------------------ batches

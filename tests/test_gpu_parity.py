@@ -1,0 +1,316 @@
+"""GPU (B200) parity tests proper: the CUDA path, called through the C ABI,
+against the fp64 oracle on the same seeded inputs and against the golden
+fixtures recorded from the live reference.
+
+Tolerances (north star): ELBO / ll within 1e-5 relative, every gradient tensor
+within 1e-4 relative in max-norm (||g - g_ref||inf / ||g_ref||inf)."""
+import numpy as np
+import pytest
+import torch
+
+import cytofpy_b200 as cy
+from cytofpy_b200.model.engine import Batch, CellEngine
+from oracle import cells_closed_form as ccf
+from tests._golden import Case, case_names, rel
+from tests._model_util import build_model, model_grads, noise_queue, replay_noise
+from tests.test_oracle_golden import kernel_inputs_from_port
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+ELBO_TOL, GRAD_TOL = 1e-5, 1e-4
+SECTIONS = ['dmu0', 'dmu1', 'dsig', 'dlogeta0', 'dlogeta1', 'dlogW', 'dZ', 'deps', 'dvm', 'dvls', 'dlqy_dvls']
+
+
+def _dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda', 0)
+
+
+def pack_globals(g, I, model_noisy):
+    eps = g['eps'] if model_noisy else np.zeros(I)
+    parts = [g['mu0'], g['mu1'], g['sig'], g['logeta0'], g['logeta1'], g['logW'], eps, g['b'], g['vm'], g['vls']]
+    return torch.tensor(np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in parts]),
+                        dtype=torch.float32)
+
+
+def pack_zmask(Z):
+    J, K = Z.shape
+    m = np.zeros(J, dtype=np.uint64)
+    for k in range(K):
+        m |= (Z[:, k] > 0.5).astype(np.uint64) << np.uint64(k)
+    return torch.tensor(m.view(np.int64))
+
+
+def check_block(blk, ref, lay, tol=GRAD_TOL):
+    for n in SECTIONS:
+        a, b = blk[lay[n][0]:lay[n][0] + lay[n][1]], ref[lay[n][0]:lay[n][0] + lay[n][1]]
+        if np.max(np.abs(b)) == 0:
+            assert np.max(np.abs(a)) < 1e-6, n
+        else:
+            assert rel(a, b) < tol, (n, rel(a, b))
+
+
+def run_kernel(eng, g, Z, rows_idx, eps, model_noisy, step=1):
+    dev = eng.device
+    counts = [len(ix) for ix in rows_idx]
+    idx = torch.tensor(np.concatenate(rows_idx).astype(np.int32), device=dev) if sum(counts) else None
+    eps_t = None if eps is None else torch.tensor(np.concatenate(eps, 0), dtype=torch.float32, device=dev)
+    batch = Batch(counts, idx, eps_t, step=step)
+    blk, ll = eng.fwdbwd(batch, pack_globals(g, eng.I, model_noisy).to(dev), pack_zmask(Z).to(dev))
+    torch.cuda.synchronize()
+    return blk.cpu().numpy().astype(np.float64), ll.cpu().numpy(), batch
+
+
+@pytest.mark.parametrize('name', case_names())
+def test_kernel_matches_closed_form_oracle(name):
+    """C-ABI call vs fp64 oracle on the golden inputs: ll, log_qy and all 11 gradient sections."""
+    c = Case(name)
+    st, cfg, idx, nz = c.state(), c.cfg(), c.idx(), c.noise()
+    _, g, rows, eps, fac = kernel_inputs_from_port(c, st, nz, cfg, idx)
+    ll_ref, lqy_ref, blk_ref, _ = ccf.cells_fwdbwd(rows, eps, g, fac, cfg['scale'],
+                                                   float(cfg['noisy_sd']), cfg['model_noisy'])
+    eng = CellEngine([t.float() for t in c.y], _dev(), c.K, c.L0, c.L1, c.noisy,
+                     float(cfg['noisy_sd']), c.scale, g['b'])
+    blk, ll, _ = run_kernel(eng, g, g['Z'], idx, eps, c.noisy)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref), (ll[0], ll_ref)
+    assert abs(ll[1] - lqy_ref) <= ELBO_TOL * max(1.0, abs(lqy_ref)), (ll[1], lqy_ref)
+    # the golden fixture itself (live reference): ll and log_qy
+    assert abs(ll[0] - c.out('ll')) <= ELBO_TOL * abs(c.out('ll'))
+    assert abs(ll[1] - c.out('log_qy')) <= ELBO_TOL * max(1.0, abs(c.out('log_qy')))
+    check_block(blk, blk_ref, ccf.block_layout(c.I, c.J, c.K, c.L0, c.L1))
+
+
+@pytest.mark.parametrize('name', case_names())
+def test_model_matches_reference_fixture(name):
+    """Model.forward + backward on the GPU vs the live-reference fixture: elbo, ll, lp, lq and
+    every .grad (global blocks and imputation parameters)."""
+    c = Case(name)
+    dev = _dev()
+    mod = build_model(c, dev)
+    with replay_noise(noise_queue(c), dev) as q:
+        elbo, ll, lp, lq = mod(c.idx())
+    assert not q
+    assert abs(elbo.item() - c.out('elbo')) <= ELBO_TOL * abs(c.out('elbo'))
+    assert abs(ll - c.out('ll')) <= ELBO_TOL * abs(c.out('ll'))
+    assert abs(lp - c.out('lp')) <= ELBO_TOL * max(1, abs(c.out('lp')))
+    assert abs(lq - c.out('lq')) <= ELBO_TOL * max(1, abs(c.out('lq')))
+    elbo.backward()
+    ref, got = c.grads(), model_grads(mod, c)
+    for k in ref:
+        assert rel(got[k], ref[k]) < GRAD_TOL, (k, rel(got[k], ref[k]))
+    assert mod.engine.launches == 2
+
+
+def test_update_trajectory_matches_reference():
+    """three reference `update` steps (Adam, lr=0.1) replayed on the GPU path"""
+    c = Case('t_traj3')
+    dev = _dev()
+    mod = build_model(c, dev)
+    opt = torch.optim.Adam(mod.parameters(), lr=float(c.z['meta_lr']))
+    elbos = []
+    for t in range(c.traj):
+        with replay_noise(noise_queue(c, t), dev):
+            elbo, fixed, ll, lp, lq = cy.model.update(opt, mod, c.idx(t))
+        elbos.append(elbo.item())
+    assert rel(elbos, c.z['out_elbos']) < ELBO_TOL
+    for k in c.keys:
+        assert rel(mod.mp[k].vp.detach().cpu().numpy(), c.z['final_vp_' + k]) < GRAD_TOL, k
+
+
+def _random_problem(I, J, K, L0, L1, N, nan_rate, seed, model_noisy=True):
+    rng = np.random.default_rng(seed)
+    y = [rng.normal(0, 3, size=(n, J)) for n in N]
+    for yi in y:
+        yi[rng.random(yi.shape) < nan_rate] = np.nan
+    dirl = lambda a, size: np.log(rng.dirichlet(a, size=size))
+    g = {'mu0': -np.cumsum(rng.gamma(2, .6, L0)), 'mu1': np.cumsum(rng.gamma(2, .6, L1)),
+         'sig': rng.uniform(.5, 1.2, I), 'logeta0': dirl(np.ones(L0), (I, J)),
+         'logeta1': dirl(np.ones(L1), (I, J)), 'logW': dirl(np.ones(K), I),
+         'Z': (rng.random((J, K)) < .5).astype(np.float64), 'eps': rng.uniform(.005, .05, I),
+         'b': np.tile(np.array([-22.19, -13.47, -1.925]), (I, 1)),
+         'vm': rng.normal(-3, .3, (I, J)), 'vls': rng.normal(-2, .3, (I, J))}
+    return y, g
+
+
+@pytest.mark.parametrize('shape', [
+    dict(I=1, J=1, K=1, L0=1, L1=1, N=[7]),              # degenerate minimum sizes
+    dict(I=2, J=5, K=3, L0=2, L1=4, N=[33, 1]),          # ragged, padded mixture variant
+    dict(I=3, J=32, K=32, L0=5, L1=5, N=[500, 300, 200]),
+    dict(I=2, J=33, K=30, L0=3, L1=3, N=[64, 65]),       # J just over one warp
+    dict(I=2, J=64, K=64, L0=8, L1=8, N=[40, 24]),       # compiled maxima
+    dict(I=32, J=8, K=4, L0=3, L1=3, N=[5] * 32),        # max number of samples
+])
+@pytest.mark.parametrize('noisy', [True, False])
+def test_kernel_random_shapes(shape, noisy):
+    """edge shapes (minimum, ragged, J/K at and just over warp width, compiled maxima)"""
+    I, J, K, L0, L1, N = (shape[k] for k in ('I', 'J', 'K', 'L0', 'L1', 'N'))
+    y, g = _random_problem(I, J, K, L0, L1, N, 0.25, seed=I * 1000 + J)
+    rng = np.random.default_rng(5)
+    idx = [rng.permutation(n)[:max(1, (2 * n) // 3)] for n in N]
+    eps = [rng.standard_normal((len(ix), J)) for ix in idx]
+    rows = [yi[ix] for yi, ix in zip(y, idx)]
+    fac = np.array([n / len(ix) for n, ix in zip(N, idx)])
+    ll_ref, lqy_ref, blk_ref, _ = ccf.cells_fwdbwd(rows, eps, g, fac, 0.7, np.sqrt(10.0), noisy)
+    eng = CellEngine([torch.tensor(t, dtype=torch.float32) for t in y], _dev(), K, L0, L1, noisy,
+                     float(np.sqrt(10.0)), 0.7, g['b'])
+    blk, ll, _ = run_kernel(eng, g, g['Z'], idx, eps, noisy)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    assert abs(ll[1] - lqy_ref) <= ELBO_TOL * max(1.0, abs(lqy_ref))
+    check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
+
+
+def test_empty_sample_and_no_missing():
+    """a sample contributing zero cells to the step, data without any NaN, eps == NULL"""
+    I, J, K, L0, L1, N = 3, 16, 7, 3, 2, [50, 40, 30]
+    y, g = _random_problem(I, J, K, L0, L1, N, 0.0, seed=3)
+    idx = [np.arange(50), np.zeros(0, np.int64), np.arange(30)[::-1].copy()]
+    rows = [yi[ix] for yi, ix in zip(y, idx)]
+    eps0 = [np.zeros((len(ix), J)) for ix in idx]
+    fac = np.array([1.0, 0.0, 1.0])
+    ll_ref, lqy_ref, blk_ref, _ = ccf.cells_fwdbwd(rows, eps0, g, fac, 1.0, np.sqrt(10.0), True)
+    eng = CellEngine([torch.tensor(t, dtype=torch.float32) for t in y], _dev(), K, L0, L1, True,
+                     float(np.sqrt(10.0)), 1.0, g['b'])
+    dev = eng.device
+    counts = [len(ix) for ix in idx]
+    it = torch.tensor(np.concatenate(idx).astype(np.int32), device=dev)
+    d_batch = Batch(counts, it, None, step=1)
+    # external mode with a NULL eps pointer is legal when nothing is missing
+    import cytofpy_b200._lib as L
+    d = eng._desc(d_batch, noise_mode=L.NOISE_EXTERNAL)
+    for i in range(I):
+        d.fac[i] = fac[i]
+    import ctypes as C
+    rc = eng.lib.cytof_elbo_fwdbwd_f32(
+        C.byref(d), C.c_void_p(eng.y_dev.data_ptr()), C.c_void_p(it.data_ptr()), C.c_void_p(0),
+        C.c_void_p(pack_globals(g, I, True).to(dev).data_ptr()), C.c_void_p(pack_zmask(g['Z']).to(dev).data_ptr()),
+        C.c_void_p(eng.grad_block.data_ptr()), C.c_void_p(eng.ll_lqy.data_ptr()),
+        C.c_void_p(eng.workspace.data_ptr()), C.c_size_t(eng.ws_bytes), C.c_void_p(0))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert abs(eng.ll_lqy[0].item() - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    assert eng.ll_lqy[1].item() == 0.0 and lqy_ref == 0.0
+    check_block(eng.grad_block.cpu().numpy().astype(np.float64), blk_ref, ccf.block_layout(I, J, K, L0, L1))
+
+
+def test_abi_rejects_bad_arguments():
+    import ctypes as C
+    import cytofpy_b200._lib as L
+    lib = L.load()
+    d = L.Desc(I=1, J=65, K=4, L0=3, L1=3)
+    assert lib.cytof_workspace_bytes(C.byref(d)) == 0
+    d = L.Desc(I=1, J=8, K=4, L0=3, L1=9)
+    assert lib.cytof_elbo_fwdbwd_f32(C.byref(d), *[C.c_void_p(0)] * 8, C.c_size_t(0), C.c_void_p(0)) == -2
+    d = L.Desc(I=1, J=8, K=4, L0=3, L1=3)
+    d.cell_begin[1] = 4
+    assert lib.cytof_elbo_fwdbwd_f32(C.byref(d), *[C.c_void_p(0)] * 8, C.c_size_t(0), C.c_void_p(0)) == -1
+    assert b'workspace' in lib.cytof_strerror(-3)
+    with pytest.raises(RuntimeError):
+        L.check(-2)
+
+
+def test_philox_mode_matches_oracle_on_emitted_noise_and_is_shard_invariant():
+    I, J, K, L0, L1, N = 2, 32, 30, 5, 3, [700, 500]
+    y, g = _random_problem(I, J, K, L0, L1, N, 0.3, seed=11)
+    dev = _dev()
+    y32 = [torch.tensor(t, dtype=torch.float32) for t in y]
+    eng = CellEngine(y32, dev, K, L0, L1, True, float(np.sqrt(10.0)), 1.0, g['b'], seed=1234)
+    batch = Batch(N, None, None, step=7)
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    blk, ll = eng.fwdbwd(batch, G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy()
+    eps = eng.philox_noise(batch).cpu().numpy().astype(np.float64)
+    # statistics of the in-kernel draws
+    assert abs(eps.mean()) < 0.02 and abs(eps.std() - 1.0) < 0.02 and np.abs(eps).max() < 6.5
+    assert abs(np.corrcoef(eps[:-1].ravel(), eps[1:].ravel())[0, 1]) < 0.02
+    eps_l = [eps[:N[0]], eps[N[0]:]]
+    ll_ref, lqy_ref, blk_ref, y_imp_ref = ccf.cells_fwdbwd(y, eps_l, g, np.ones(I), 1.0, np.sqrt(10.0), True)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    assert abs(ll[1] - lqy_ref) <= ELBO_TOL * abs(lqy_ref)
+    check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
+    # imputed matrix from the emit kernel
+    y_imp = eng.impute(batch, G).cpu().numpy()
+    assert np.allclose(y_imp, np.concatenate(y_imp_ref), rtol=2e-6, atol=2e-6)
+    # a different step gives different draws; the same step the same draws
+    assert not np.allclose(eng.philox_noise(Batch(N, None, None, step=8)).cpu().numpy(), eps)
+    assert np.array_equal(eng.philox_noise(Batch(N, None, None, step=7)).cpu().numpy(), eps.astype(np.float32))
+    # shard invariance: two "ranks" each holding half of every sample see the same draws for the
+    # same global rows, and their partial results add up to the single-rank result
+    tot_blk, tot_ll = 0, 0
+    for r in range(2):
+        lo = [0 if r == 0 else n // 2 for n in N]
+        hi = [n // 2 if r == 0 else n for n in N]
+        part = [t[a:b] for t, a, b in zip(y32, lo, hi)]
+        e2 = CellEngine(part, dev, K, L0, L1, True, float(np.sqrt(10.0)), 1.0, g['b'],
+                        N_global=N, row_global=lo, seed=1234)
+        b2 = Batch([b - a for a, b in zip(lo, hi)], None, None, step=7)
+        bb, l2 = e2.fwdbwd(b2, G, zm, counts_global=N)
+        tot_blk = tot_blk + bb.cpu().numpy().astype(np.float64)
+        tot_ll = tot_ll + l2.cpu().numpy()
+    assert abs(tot_ll[0] - ll[0]) <= 1e-6 * abs(ll[0])
+    check_block(tot_blk, blk, ccf.block_layout(I, J, K, L0, L1), tol=2e-5)
+
+
+def test_results_are_bitwise_reproducible():
+    I, J, K, L0, L1, N = 3, 32, 30, 5, 3, [3000, 2000, 1000]
+    y, g = _random_problem(I, J, K, L0, L1, N, 0.2, seed=21)
+    eng = CellEngine([torch.tensor(t, dtype=torch.float32) for t in y], _dev(), K, L0, L1, True,
+                     float(np.sqrt(10.0)), 1.0, g['b'], seed=5)
+    G, zm = pack_globals(g, I, True).to(eng.device), pack_zmask(g['Z']).to(eng.device)
+    outs = []
+    for _ in range(3):
+        blk, ll = eng.fwdbwd(Batch(N, None, None, step=3), G, zm)
+        outs.append((blk.clone(), ll.clone()))
+    for b, l in outs[1:]:
+        assert torch.equal(b, outs[0][0]) and torch.equal(l, outs[0][1])
+
+
+def test_full_size_properties_cfg4_shape():
+    """BASELINE cfg4 shape at full size (I=8 x 125,000 cells, J=32, K=30, L=5/5), too big for the
+    fp64 oracle in seconds, checked through size-independent properties:
+      additivity  — ll / gradient block of all cells = sum over two disjoint halves
+      scaling     — doubling fac_i doubles ll and the gradient block
+      order       — a permutation of the cells (gather path) leaves the result unchanged
+      spot check  — a 2,000-cell slice agrees with the fp64 oracle."""
+    I, J, K, L0, L1 = 8, 32, 30, 5, 5
+    N = [125000] * I
+    dev = _dev()
+    s = cy.util.synth_cytof(N, J, [100.] * 5, L0, L1, seed=0)
+    _, g = _random_problem(I, J, K, L0, L1, [1] * I, 0.0, seed=31)
+    g['mu0'], g['mu1'] = -(np.arange(L0) + 1.5), np.arange(L1) + 1.5
+    y32 = [torch.from_numpy(a) for a in s['y']]
+    eng = CellEngine(y32, dev, K, L0, L1, True, float(np.sqrt(10.0)), 1.0, g['b'], seed=9)
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    lay = ccf.block_layout(I, J, K, L0, L1)
+    blk, ll = eng.fwdbwd(Batch(N, None, None, step=1), G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy().copy()
+    assert np.isfinite(blk).all() and np.isfinite(ll).all()
+    # additivity over halves (idx path)
+    tot_b, tot_l = 0, 0
+    for h in range(2):
+        idx = torch.cat([torch.arange(h * 62500, (h + 1) * 62500, dtype=torch.int32) for _ in range(I)]).to(dev)
+        b = Batch([62500] * I, idx, None, step=1)
+        d = eng._desc(b)
+        bb, l2 = eng.fwdbwd(b, G, zm, counts_global=N)      # fac stays N_i/N_i = 1
+        tot_b = tot_b + bb.cpu().numpy().astype(np.float64)
+        tot_l = tot_l + l2.cpu().numpy()
+    assert abs(tot_l[0] - ll[0]) <= 1e-7 * abs(ll[0])
+    check_block(tot_b, blk, lay, tol=2e-5)
+    # permutation invariance
+    gen = torch.Generator().manual_seed(0)
+    perm = torch.cat([torch.randperm(n, generator=gen).to(torch.int32) for n in N]).to(dev)
+    bb, l2 = eng.fwdbwd(Batch(N, perm, None, step=1), G, zm)
+    assert abs(l2[0].item() - ll[0]) <= 1e-7 * abs(ll[0])
+    check_block(bb.cpu().numpy().astype(np.float64), blk, lay, tol=2e-5)
+    # scaling with fac
+    bb, l2 = eng.fwdbwd(Batch(N, None, None, step=1), G, zm, counts_global=[n // 2 for n in N])
+    assert abs(l2[0].item() - 2 * ll[0]) <= 1e-9 * abs(ll[0])
+    check_block(bb.cpu().numpy().astype(np.float64), 2 * blk, lay, tol=1e-6)
+    # spot check against the oracle
+    idx = [np.arange(1000, 1250) for _ in range(I)]
+    rows = [s['y'][i][idx[i]].astype(np.float64) for i in range(I)]
+    fac = np.array([n / 250 for n in N])
+    ll_ref, _, blk_ref, _ = ccf.cells_fwdbwd(rows, [np.zeros((250, J))] * I, g, fac, 1.0, np.sqrt(10.0), True)
+    it = torch.tensor(np.concatenate(idx).astype(np.int32), device=dev)
+    bb, l2 = eng.fwdbwd(Batch([250] * I, it, None, step=1), G, zm)
+    assert abs(l2[0].item() - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    check_block(bb.cpu().numpy().astype(np.float64), blk_ref, lay)

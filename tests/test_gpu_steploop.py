@@ -1,0 +1,106 @@
+"""GPU: the small step-loop kernels behind the C ABI — fused Adam with NaN scrub
+(reference fit.py:24-30,83) and the without-replacement minibatch sampler
+(reference fit.py:96-102) — plus an end-to-end `fit` smoke run."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cytofpy_b200 as cy
+from cytofpy_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def test_adam_kernel_matches_torch_adam_and_scrubs_nan():
+    dev = torch.device('cuda', 0)
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    n, n_scrub = 3528, 3336
+    p0 = torch.randn(n, dtype=F64, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.1)
+    p = p0.clone().to(dev)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    for t in range(1, 6):
+        grad = torch.randn(n, dtype=F64, generator=g) * 10
+        ref.grad = (grad * -0.001).clone()
+        if t == 3:
+            grad[5] = float('nan')          # inside the scrubbed range
+            ref.grad[5] = 0.0
+        opt.step()
+        use_dev_counter = t >= 4
+        if t == 4:
+            step_dev.fill_(3)
+        _lib.check(lib.cytof_adam_step_f64(_p(p), _p(grad.to(dev)), _p(m), _p(v), n, n_scrub, -0.001, 0.1,
+                                           0.9, 0.999, 1e-8, t, _p(step_dev) if use_dev_counter else _p(None),
+                                           _p(flag), C.c_void_p(0)))
+        torch.cuda.synchronize()
+        assert flag.item() == (1 if t >= 3 else 0)
+        assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-12, atol=1e-14), t
+    assert step_dev.item() == 5
+    # a NaN outside the scrubbed range propagates (reference leaves imputation grads alone)
+    grad = torch.zeros(n, dtype=F64)
+    grad[n - 1] = float('nan')
+    _lib.check(lib.cytof_adam_step_f64(_p(p), _p(grad.to(dev)), _p(m), _p(v), n, n_scrub, 1.0, 0.1, 0.9,
+                                       0.999, 1e-8, 6, _p(None), _p(None), C.c_void_p(0)))
+    assert torch.isnan(p[n - 1]).item() and not torch.isnan(p[:n - 1]).any().item()
+
+
+@pytest.mark.parametrize('N,m', [(40000, 2000), (41474, 500), (17, 16), (2, 1), (1000003, 1000)])
+def test_sampler_without_replacement(N, m):
+    dev = torch.device('cuda', 0)
+    lib = _lib.load()
+    out = torch.empty(m, dtype=torch.int32, device=dev)
+
+    def draw(seed, step, sample):
+        _lib.check(lib.cytof_sample_minibatch(N, m, seed, step, sample, _p(out), C.c_void_p(0)))
+        return out.cpu().numpy().copy()
+    a = draw(1, 0, 0)
+    assert a.min() >= 0 and a.max() < N and len(np.unique(a)) == m        # distinct, in range
+    assert np.array_equal(a, draw(1, 0, 0))                               # deterministic per key
+    if N > 100:
+        assert not np.array_equal(a, draw(1, 1, 0)) and not np.array_equal(a, draw(1, 0, 1))
+        assert not np.array_equal(a, draw(2, 0, 0))
+
+
+def test_sampler_is_roughly_uniform_and_full_batch_is_identity():
+    dev = torch.device('cuda', 0)
+    lib = _lib.load()
+    N, m = 1000, 100
+    out = torch.empty(m, dtype=torch.int32, device=dev)
+    hits = np.zeros(N)
+    for step in range(2000):
+        _lib.check(lib.cytof_sample_minibatch(N, m, 7, step, 0, _p(out), C.c_void_p(0)))
+        hits[out.cpu().numpy()] += 1
+    # each index expected 200 times, sd ~ 13.4; allow 6 sigma
+    assert abs(hits.mean() - 200) < 1e-9 and hits.min() > 120 and hits.max() < 280
+    full = torch.empty(N, dtype=torch.int32, device=dev)
+    _lib.check(lib.cytof_sample_minibatch(N, N + 5, 7, 0, 0, _p(full), C.c_void_p(0)))
+    assert np.array_equal(full.cpu().numpy(), np.arange(N))
+
+
+def test_fit_runs_and_improves_elbo(capsys):
+    """the reference's own smoke test (tests/test_model.py:12-43) against the drop-in, with an
+    assertion the reference lacks: the ELBO must improve."""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    data = cy.util.simdata(N=[300, 100, 200], L0=3, L1=3, J=8, a_W=[100.] * 5, seed=0)
+    y = [t.clone() for t in data['data']['y']]
+    pri = cy.model.default_priors(y, K=10, L=[3, 3], y_bounds=[-5., -3.5, -2.])
+    out = cy.model.fit(y, max_iter=60, lr=1e-1, print_freq=20, eps_conv=1e-6, priors=pri,
+                       minibatch_size=100, tau=0.1, verbose=0, seed=1)
+    assert set(out) == {'elbo', 'trace', 'mp', 'tau', 'vae', 'use_stick_break', 'y', 'priors', 'model_noisy'}
+    e = np.array(out['elbo'])
+    assert len(e) == 61 and np.isfinite(e).all()
+    assert e[-10:].mean() > e[:3].mean() + 1000
+    assert len(out['trace']) >= 30 and 'W' in out['trace'][0]
+    assert out['trace'][0]['W'].dist().mean.shape == (3, 9)
