@@ -47,7 +47,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB_PATH
+    # CYTOF_B200_LIB selects a tuning build of the same sources (tools/kbench.py); never a fallback
+    return os.environ.get('CYTOF_B200_LIB') or _build.LIB_PATH
 
 
 def load():

@@ -31,19 +31,21 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA library if missing or older than its sources."""
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile the CUDA library if missing or older than its sources.  `defines` / `out`
+    build a tuning variant under another name (tools/kbench.py)."""
+    if out is None and not force and not _stale():
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
+    target = out or LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+          ['-D' + d for d in defines] + ['-o', target] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == '__main__':

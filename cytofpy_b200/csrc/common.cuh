@@ -41,6 +41,21 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// sm_100a warp reductions that do not go through the shuffle network:
+// CREDUX.MAX.F32 (one instruction, result in a uniform register) ...
+__device__ __forceinline__ float warp_max_redux(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+// ... and an exact-order-independent sum of values in [0, 64) via 2^-24 fixed point + REDUX.SUM
+// (abs. error <= 32 * 2^-25; used for softmax denominators whose largest term is 1).
+__device__ __forceinline__ float warp_sum_unit(float v) {
+  unsigned q = __float2uint_rn(v * 16777216.0f), r;
+  asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(q));
+  return (float)r * (1.0f / 16777216.0f);
+}
+
 // streaming 4-byte load that does not pollute L1 (each y row is read exactly once)
 __device__ __forceinline__ float ld_stream(const float* p) {
   float r;
@@ -153,7 +168,7 @@ struct ElboParams {
   float* partials;
   float* y_out;  // impute-emit mode only
   int I, J, K, L0, L1;
-  int noise_mode;
+  int noise_mode, model_noisy;
   float noisy_sd, scale;
   unsigned long long seed;
   uint32_t step;

@@ -21,10 +21,20 @@
 
 namespace cytof {
 
+// build-time tuning knobs (see tools/kbench.py): resident CTAs/SM the register allocator must
+// allow for the one-marker-per-lane variants, and whether Z is kept as 0/1 floats (FFMA) or as
+// bit masks (predicated FADD)
+#ifndef CYTOF_MINBLOCKS
+#define CYTOF_MINBLOCKS 1
+#endif
+#ifndef CYTOF_ZFLOAT
+#define CYTOF_ZFLOAT 1
+#endif
+
 template <int LM0, int LM1, int JP, int KP, bool NOISY>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (JP == 1 && KP == 1) ? CYTOF_MINBLOCKS : 1)
 elbo_fwdbwd_kernel(const ElboParams p) {
-  constexpr bool ZF = (JP == 1 && KP == 1);  // Z rows/columns held as float registers
+  constexpr bool ZF = (JP == 1 && KP == 1) && CYTOF_ZFLOAT;  // Z rows/columns as float registers
   constexpr int JW = JP * 32, KW = KP * 32;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
@@ -256,14 +266,14 @@ elbo_fwdbwd_kernel(const ElboParams p) {
       f[kp] = ((a[0] + a[1]) + (a[2] + a[3])) + a0sum + lw2[kp];
       mx = fmaxf(mx, f[kp]);
     }
-    mx = warp_max(mx);
+    mx = warp_max_redux(mx);
     float ex[KP], s = 0.f;
 #pragma unroll
     for (int kp = 0; kp < KP; ++kp) {
       ex[kp] = fast_ex2(f[kp] - mx);
       s += ex[kp];
     }
-    s = warp_sum(s);
+    s = warp_sum_unit(s);   // every term is in [0, KP]
     const float lse2 = mx + fast_lg2(s);
     const float rinv = fast_rcp(s);
 
@@ -329,7 +339,7 @@ elbo_fwdbwd_kernel(const ElboParams p) {
         sw0[jp][l] += w;
         swd0[l] += wd;
         swdd = fmaf(wd, d, swdd);
-        wdsum += wd;
+        e0[jp][l] = wd;   // kept for d ll / d y (only consumed when the row has missing entries)
       }
 #pragma unroll
       for (int l = 0; l < LM1; ++l) {
@@ -339,10 +349,14 @@ elbo_fwdbwd_kernel(const ElboParams p) {
         sw1[jp][l] += w;
         swd1[l] += wd;
         swdd = fmaf(wd, d, swdd);
-        wdsum += wd;
+        e1[jp][l] = wd;
       }
       // logistic missingness (Model.py:269-274) and d/dy chain into the imputation parameters
       if (anym) {
+#pragma unroll
+        for (int l = 0; l < LM0; ++l) wdsum += e0[jp][l];
+#pragma unroll
+        for (int l = 0; l < LM1; ++l) wdsum += e1[jp][l];
         const float u = fmaf(fmaf(b2, yv[jp], b1), yv[jp], b0);
         const float t = fast_ex2(-fabsf(u) * kLog2e);
         const float rr = fast_rcp(1.f + t);
@@ -481,7 +495,7 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   } else if (t < bl.dvm) {  // deps_i = -sum fac rho/(1-eps) + sum fac (1-rho)/eps
     const int i = t - bl.deps;
     const double e = (double)G[gl.eps + i];
-    r = -sum_sample(i, pl.sc + 1) / (1.0 - e) + sum_sample(i, pl.sc + 2) / e;
+    r = p.model_noisy ? -sum_sample(i, pl.sc + 1) / (1.0 - e) + sum_sample(i, pl.sc + 2) / e : 0.0;
   } else if (t < bl.dvls) {
     const int q = t - bl.dvm, i = q / J, j = q % J;
     r = sum_sample(i, pl.dvm + j);
@@ -598,6 +612,7 @@ int validate_desc(const cytof_desc* d) {
 void fill_params(const cytof_desc* d, ElboParams* p) {
   p->I = d->I; p->J = d->J; p->K = d->K; p->L0 = d->L0; p->L1 = d->L1;
   p->noise_mode = d->noise_mode;
+  p->model_noisy = d->model_noisy;
   p->noisy_sd = d->noisy_sd;
   p->scale = d->scale;
   p->seed = d->seed;
@@ -610,24 +625,37 @@ void fill_params(const cytof_desc* d, ElboParams* p) {
   }
 }
 
-// Splits the grid over samples proportionally to their cell counts (>= 1 CTA per non-empty
-// sample) so that a CTA never mixes samples.
+// Splits the grid over samples so that a CTA never mixes samples: every non-empty sample gets
+// one CTA, the rest go one at a time to the sample with the most cells per CTA (min-max
+// optimal).  The total never exceeds SMs x resident CTAs/SM: exactly one wave, no tail.
 static int plan_grid(const cytof_desc* d, ElboParams* p, int occ) {
   const long long C = d->cell_begin[d->I];
   const int cap = device_sm_count() * occ;
   long long want = (C + (long long)kWarps * kMinCellsPerWarp - 1) / ((long long)kWarps * kMinCellsPerWarp);
   if (want > cap) want = cap;
-  if (want < 1) want = 1;
+  int n[CYTOF_MAX_SAMPLES];
+  long long B[CYTOF_MAX_SAMPLES];
+  int used = 0;
+  for (int i = 0; i < d->I; ++i) {
+    B[i] = d->cell_begin[i + 1] - d->cell_begin[i];
+    n[i] = B[i] > 0 ? 1 : 0;
+    used += n[i];
+  }
+  for (; used < want; ++used) {
+    int best = -1;
+    double load = 0.0;
+    for (int i = 0; i < d->I; ++i) {
+      if (n[i] == 0 || n[i] >= B[i]) continue;
+      const double li = (double)B[i] / n[i];
+      if (li > load) { load = li; best = i; }
+    }
+    if (best < 0) break;
+    ++n[best];
+  }
   int b = 0;
   for (int i = 0; i < d->I; ++i) {
     p->blk_begin[i] = b;
-    const long long Bi = d->cell_begin[i + 1] - d->cell_begin[i];
-    if (Bi > 0) {
-      long long n = (want * Bi + C / 2) / (C > 0 ? C : 1);
-      if (n < 1) n = 1;
-      if (n > Bi) n = Bi;
-      b += (int)n;
-    }
+    b += n[i];
   }
   p->blk_begin[d->I] = b;
   p->nblocks = b;

@@ -44,8 +44,10 @@ def pack_zmask(Z):
 def check_block(blk, ref, lay, tol=GRAD_TOL):
     for n in SECTIONS:
         a, b = blk[lay[n][0]:lay[n][0] + lay[n][1]], ref[lay[n][0]:lay[n][0] + lay[n][1]]
-        if np.max(np.abs(b)) == 0:
-            assert np.max(np.abs(a)) < 1e-6, n
+        if np.max(np.abs(b)) < 1e-25:
+            # below fp32 range (e.g. 1e-153 responsibilities at a fresh init):
+            # the fp32 kernel flushes these to zero
+            assert np.max(np.abs(a)) < 1e-20, n
         else:
             assert rel(a, b) < tol, (n, rel(a, b))
 
@@ -180,9 +182,10 @@ def test_empty_sample_and_no_missing():
     for i in range(I):
         d.fac[i] = fac[i]
     import ctypes as C
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)     # keep alive
     rc = eng.lib.cytof_elbo_fwdbwd_f32(
         C.byref(d), C.c_void_p(eng.y_dev.data_ptr()), C.c_void_p(it.data_ptr()), C.c_void_p(0),
-        C.c_void_p(pack_globals(g, I, True).to(dev).data_ptr()), C.c_void_p(pack_zmask(g['Z']).to(dev).data_ptr()),
+        C.c_void_p(G.data_ptr()), C.c_void_p(zm.data_ptr()),
         C.c_void_p(eng.grad_block.data_ptr()), C.c_void_p(eng.ll_lqy.data_ptr()),
         C.c_void_p(eng.workspace.data_ptr()), C.c_size_t(eng.ws_bytes), C.c_void_p(0))
     assert rc == 0
