@@ -7,7 +7,7 @@
 A "step" is one full `update` of the reference (fit.py:32-48): draw the global
 sample, transforms, per-cell ELBO forward+backward over ONE batch (the fused
 CUDA kernel), log prior, entropy, backward to every variational parameter, NaN
-scrub and the Adam step.  The default workload is BASELINE.json configs[3]
+scrub and the Adam step — here 4 kernel launches (cytofpy_b200/model/fused.py).  The default workload is BASELINE.json configs[3]
 ("cfg4": full batch, I=8, J=32, K=30, L=5/5) — the configuration the metric
 string names — with 1,000,000 cells PER GPU (weak scaling: rank r holds rows
 [r*125000, (r+1)*125000) of each of the 8 samples; one all-reduce of the
@@ -158,8 +158,13 @@ def run_ours(args, w, rank, world, local_rank):
     torch.manual_seed(1)
     model = cy.model.Model(y=y, priors=priors, verbose=-1, device=dev, noise='philox', seed=1,
                            N_global=N_global, row_global=[rank * n] * I, dist_group=group, **w['kw'])
-    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    from cytofpy_b200.model.fused import FusedStep
+    fs = FusedStep(model, lr=1e-2, seed=1)       # the path cytofpy_b200.model.fit drives
     mb = w['mb']
+    n_sampler = 0 if mb is None else I
+
+    def one_step(t):
+        return fs.step(draw_idx(t))
 
     def draw_idx(t):
         return [range(n)] * I if mb is None else cy.model.device_minibatch(model, mb, t, 1)
@@ -175,21 +180,21 @@ def run_ours(args, w, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     for t in range(args.warmup):
-        cy.model.update(opt, model, draw_idx(t))
+        one_step(t)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = eng.launches
+    launches0 = fs.launches
     for t in range(args.steps):
         flush.fill_(t & 0xff)                                   # evict y from the 126 MB L2
         ev[t][0].record()
-        cy.model.update(opt, model, draw_idx(args.warmup + t))
+        one_step(args.warmup + t)
         ev[t][1].record()
     barrier()
     sampler.stop_flag = True
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    launches = eng.launches - launches0
+    launches = fs.launches - launches0 + n_sampler * args.steps
 
     # ---- dominant kernel alone (CUDA events on the launching stream, L2 flushed)
     model._step += 1
@@ -234,8 +239,7 @@ def run_ours(args, w, rank, world, local_rank):
             eng.y_dev[:stage.shape[0]].copy_(stage, non_blocking=True)
             idx = [torch.arange(i * mb, (i + 1) * mb, dtype=torch.int32) - i * n for i in range(I)]
             idx = [ix.to(dev) for ix in idx]
-        elbo, *_ = cy.model.update(opt, model, idx)
-        _ = elbo.item()
+        _ = fs.step(idx).tolist()                                # 40-byte read-back of elbo/ll/lp/lq
         b.record()
         e_ev.append((a, b))
     barrier()
@@ -265,7 +269,7 @@ def run_ours(args, w, rank, world, local_rank):
                        'parallelism': 'cells sharded x%d, all-reduce of gradient block' % world,
                        'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox'},
             'e2e': {'value': cells_step * world / (e2e_ms * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms},
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_kernel (+finalize)', 'achieved': achieved,

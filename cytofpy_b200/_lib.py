@@ -26,6 +26,22 @@ class Desc(C.Structure):
     ]
 
 
+class GlobalDesc(C.Structure):
+    """mirror of `struct cytof_global_desc`"""
+    _fields_ = [
+        ('I', C.c_int32), ('J', C.c_int32), ('K', C.c_int32), ('L0', C.c_int32), ('L1', C.c_int32),
+        ('model_noisy', C.c_int32), ('use_stick_break', C.c_int32), ('noise_mode', C.c_int32),
+        ('sig2_family', C.c_int32), ('reserved0', C.c_int32),
+        ('tau', C.c_double),
+        ('delta0', C.c_double * 2), ('delta1', C.c_double * 2), ('sig2', C.c_double * 2),
+        ('alpha', C.c_double * 2), ('eps', C.c_double * 2),
+        ('eta0_conc', C.c_double * MAX_L), ('eta1_conc', C.c_double * MAX_L), ('W_conc', C.c_double * MAX_K),
+        ('seed', C.c_uint64), ('step', C.c_uint64),
+        ('grad_scale', C.c_double), ('lr', C.c_double), ('beta1', C.c_double), ('beta2', C.c_double),
+        ('adam_eps', C.c_double), ('adam_step', C.c_int64),
+    ]
+
+
 _P = C.c_void_p
 _PROTOS = {
     'cytof_abi_version': (C.c_int, []),
@@ -35,6 +51,11 @@ _PROTOS = {
     'cytof_grad_block_layout': (C.c_int, [C.POINTER(Desc), C.POINTER(C.c_int64)]),
     'cytof_workspace_bytes': (C.c_size_t, [C.POINTER(Desc)]),
     'cytof_elbo_fwdbwd_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'cytof_elbo_fwdbwd_packed': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'cytof_global_sizes': (C.c_int, [C.POINTER(GlobalDesc), C.POINTER(C.c_int64)]),
+    'cytof_global_fwd_f64': (C.c_int, [C.POINTER(GlobalDesc), _P, _P, _P, _P, _P, _P, _P]),
+    'cytof_global_bwd_adam_f64': (C.c_int, [C.POINTER(GlobalDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                            C.c_int32, _P]),
     'cytof_impute_emit_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P]),
     'cytof_noise_emit_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P]),
     'cytof_adam_step_f64': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double,

@@ -11,7 +11,16 @@ int validate_desc(const cytof_desc* d);
 size_t workspace_bytes(const cytof_desc* d);
 int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
-                  void* workspace, size_t workspace_bytes_, cudaStream_t stream, cudaError_t* err);
+                  double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
+                  cudaError_t* err);
+struct GlobalParams;
+int global_sizes(const cytof_global_desc* g, int64_t out[4]);
+int launch_global_fwd(const cytof_global_desc* g, const double* theta, const double* eps_in, double* stash,
+                      float* globals, uint64_t* zmask, double* scalars, cudaStream_t s, cudaError_t* err);
+int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, const double* packed,
+                      const double* scalars_in, double* adam_m, double* adam_v, double* grad_out,
+                      double* out_scalars, int64_t* step_dev, int32_t* flag, int do_update, cudaStream_t s,
+                      cudaError_t* err);
 int launch_emit(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                 const float* globals, float* y_out, float* eps_out, cudaStream_t stream, cudaError_t* err);
 
@@ -128,8 +137,51 @@ int cytof_elbo_fwdbwd_f32(const cytof_desc* d, const float* y, const int32_t* id
       (reinterpret_cast<uintptr_t>(y) & 3) || (reinterpret_cast<uintptr_t>(globals) & 3))
     return CYTOF_EALIGN;
   cudaError_t err = cudaSuccess;
-  rc = launch_fwdbwd(d, y, idx, eps, globals, zmask, grad_block, ll_lqy, workspace, workspace_bytes_,
+  rc = launch_fwdbwd(d, y, idx, eps, globals, zmask, grad_block, ll_lqy, nullptr, workspace,
+                     workspace_bytes_, (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_elbo_fwdbwd_packed(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                             const float* globals, const uint64_t* zmask, double* packed,
+                             void* workspace, size_t workspace_bytes_, void* stream) {
+  int rc = validate_desc(d);
+  if (rc != CYTOF_OK) return rc;
+  if (!globals || !zmask || !packed || !workspace) return CYTOF_EINVAL;
+  if (!y && d->cell_begin[d->I] > 0) return CYTOF_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(packed) & 7) || (reinterpret_cast<uintptr_t>(zmask) & 7)) return CYTOF_EALIGN;
+  cudaError_t err = cudaSuccess;
+  rc = launch_fwdbwd(d, y, idx, eps, globals, zmask, nullptr, nullptr, packed, workspace, workspace_bytes_,
                      (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_global_sizes(const cytof_global_desc* g, int64_t out[4]) {
+  if (!g || !out) return CYTOF_EINVAL;
+  return global_sizes(g, out);
+}
+
+int cytof_global_fwd_f64(const cytof_global_desc* g, const double* theta, const double* eps_in,
+                         double* stash, float* globals, uint64_t* zmask, double* scalars, void* stream) {
+  if (!g || !theta || !stash || !globals || !zmask || !scalars) return CYTOF_EINVAL;
+  if (g->noise_mode == CYTOF_NOISE_EXTERNAL && !eps_in) return CYTOF_EINVAL;
+  cudaError_t err = cudaSuccess;
+  const int rc = launch_global_fwd(g, theta, eps_in, stash, globals, zmask, scalars, (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_global_bwd_adam_f64(const cytof_global_desc* g, double* theta, double* stash,
+                              const double* packed, const double* scalars_in, double* adam_m,
+                              double* adam_v, double* grad_out, double* out_scalars,
+                              int64_t* step_dev, int32_t* flag, int32_t do_update, void* stream) {
+  if (!g || !theta || !stash || !packed || !scalars_in || !out_scalars) return CYTOF_EINVAL;
+  if (do_update && (!adam_m || !adam_v)) return CYTOF_EINVAL;
+  cudaError_t err = cudaSuccess;
+  const int rc = launch_global_bwd(g, theta, stash, packed, scalars_in, adam_m, adam_v, grad_out, out_scalars,
+                                   step_dev, flag, do_update, (cudaStream_t)stream, &err);
   if (rc == CYTOF_ECUDA) set_cuda_err(err);
   return rc;
 }

@@ -440,7 +440,7 @@ elbo_fwdbwd_kernel(const ElboParams p) {
 // One thread per output of the gradient block (+ ll, log_qy): sums the per-CTA records of
 // the relevant sample(s) in fp64, fixed order, and applies the per-sample scalings.
 __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
-                                     double* __restrict__ ll_lqy) {
+                                     double* __restrict__ ll_lqy, double* __restrict__ packed) {
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const PartialLayout pl = partial_layout(J, K, L0, L1);
@@ -459,7 +459,8 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     double a = 0.0;
     for (int b = 0; b < p.nblocks; ++b)
       a += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
-    ll_lqy[which] = a;
+    if (ll_lqy) ll_lqy[which] = a;
+    if (packed) packed[t] = a;
     return;
   }
   double r = 0.0;
@@ -506,7 +507,8 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     const int q = t - bl.dlq, i = q / J, j = q % J;
     r = -(double)p.fac[i] * (double)p.scale * sum_sample(i, pl.nm + j);
   }
-  grad_block[t] = (float)r;
+  if (grad_block) grad_block[t] = (float)r;
+  if (packed) packed[t] = r;
 }
 
 // y_out[C,J] = imputed minibatch (vae.py:33); eps_out[C,J] = the Philox draws.
@@ -669,7 +671,8 @@ size_t workspace_bytes(const cytof_desc* d) {
 
 int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
-                  void* workspace, size_t workspace_bytes_, cudaStream_t stream, cudaError_t* err) {
+                  double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
+                  cudaError_t* err) {
   const Variant* v = pick_variant(d->J, d->K, d->L0, d->L1);
   ElboParams p;
   fill_params(d, &p);
@@ -695,7 +698,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     if (*err != cudaSuccess) return CYTOF_ECUDA;
   }
   const int nout = bl.total + 2;
-  elbo_finalize_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(p, grad_block, ll_lqy);
+  elbo_finalize_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(p, grad_block, ll_lqy, packed);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }

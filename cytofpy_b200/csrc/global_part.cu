@@ -1,0 +1,444 @@
+// The O(3.5k-scalar) "global part" of one ADVI step as two single-CTA fp64 kernels that
+// bracket the fused per-cell kernel, replacing ~5,000 tiny ATen dispatches of the reference:
+//
+//   global_fwd_kernel      reference model_param.py:46-55 (reparameterised sample of every
+//                          global block), :57-71 (exp / sigmoid / stick-breaking), Model.py:212,
+//                          223,227,236-243 (sig, mu0, mu1, cumprod(v), Z = 1[v > H] in fp64),
+//                          Model.py:289-304 (log prior + log|det J|), model_param.py:91-92
+//                          (entropy term).  Emits the fp32 `globals` + `zmask` the cell kernel
+//                          consumes and the scalars lp, lq_global.
+//   global_bwd_adam_kernel the autograd backward of all of the above (closed forms below), the
+//                          chain from the cell kernel's gradient block to every variational
+//                          parameter, loss = -elbo / Nsum (fit.py:34), the NaN scrub of the
+//                          global blocks (fit.py:24-30,44-45) and the Adam update (fit.py:47,83).
+//
+// theta layout (fp64, one flat buffer): for every block in the reference's registration order
+//   delta0 | delta1 | [eps] | sig2 | eta0 | eta1 | W | alpha | v | H
+// its means m[size] then its log-sds log_s[size] (= vp[0], vp[1] contiguous), followed by, per
+// sample, the imputation mean[J] and log_sd[J] (Model.py:202-208).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cytof {
+
+enum { B_DELTA0 = 0, B_DELTA1, B_EPS, B_SIG2, B_ETA0, B_ETA1, B_W, B_ALPHA, B_V, B_H, B_COUNT };
+
+struct GlobalParams {
+  int I, J, K, L0, L1;
+  int model_noisy, use_stick_break;
+  int noise_mode;      // CYTOF_NOISE_EXTERNAL: eps_in[R] supplied; CYTOF_NOISE_PHILOX: drawn here
+  int sig2_family;     // 0 LogNormal(p0 = loc, p1 = scale), 1 Gamma(p0 = conc, p1 = rate)
+  double tau;
+  double delta0_a, delta0_b, delta1_a, delta1_b, sig2_p0, sig2_p1, alpha_a, alpha_b, eps_a, eps_b;
+  double eta0_c[CYTOF_MAX_L], eta1_c[CYTOF_MAX_L], W_c[CYTOF_MAX_K];
+  unsigned long long seed, step;
+  // real-vector layout: offset of each block in the R-vector (noise / reals) and in theta
+  int roff[B_COUNT + 1];   // roff[b]..roff[b+1]
+  int toff[B_COUNT];       // theta offset of m; log_s at toff + size
+  int n_global;            // = 2 R
+  int vae_off;             // theta offset of the imputation parameters
+  // Adam + loss scaling
+  double grad_scale, lr, beta1, beta2, adam_eps;
+  long long step_host;
+};
+
+__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double log_sigmoid_d(double x) { return -(fmax(-x, 0.0) + log1p(exp(-fabs(x)))); }
+__device__ __forceinline__ bool squashed(int b) { return b == B_EPS || b == B_ETA0 || b == B_ETA1 || b == B_W || b == B_V || b == B_H; }
+__device__ __forceinline__ int block_of(const GlobalParams& p, int q) {
+  int b = 0;
+  while (b + 1 < B_COUNT && q >= p.roff[b + 1]) ++b;
+  return b;
+}
+
+// fp64 standard normal from Philox (Box-Muller, 53-bit uniform)
+__device__ __forceinline__ double philox_normal_d(unsigned long long seed, unsigned long long step, unsigned q) {
+  uint32_t c[4] = {q, 0x5eed5eedu, (uint32_t)step, (uint32_t)(step >> 32)};
+  philox4x32_10(c, (uint32_t)seed ^ 0x9e3779b9u, (uint32_t)(seed >> 32));
+  const unsigned long long a = ((unsigned long long)c[0] << 21) ^ (unsigned long long)(c[1] >> 11);
+  const double u1 = ((double)(a & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)c[2] * 4294967296.0 + (double)c[3] + 0.5) * (1.0 / 18446744073709551616.0);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__device__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];   // fixed order: reproducible
+  return t;
+}
+
+// stick-breaking of one row x[0..n) -> log y[0..n]  (torch StickBreakingTransform incl. its
+// clipped sigmoid); returns log|det J| of the row
+__device__ double stick_row(const double* x, int n, double* logy, double* zbuf) {
+  const double tiny = 2.2250738585072014e-308, one_m_eps = 1.0 - 2.220446049250313e-16;
+  double acc = 0.0, ld = 0.0;
+  for (int k = 0; k < n; ++k) {
+    double z = sigmoid_d(x[k] - log((double)(n - k)));
+    z = fmin(fmax(z, tiny), one_m_eps);
+    if (zbuf) zbuf[k] = z;
+    const double l1mz = log1p(-z);
+    logy[k] = log(z) + acc;
+    ld += l1mz + logy[k];
+    acc += l1mz;
+  }
+  logy[n] = acc;
+  return ld;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const double* __restrict__ eps_in,
+                  double* __restrict__ real, double* __restrict__ eps_out, float* __restrict__ globals,
+                  unsigned long long* __restrict__ zmask, double* __restrict__ scalars /* lp, lq_global */) {
+  __shared__ double sh[32];
+  __shared__ double s_vc[CYTOF_MAX_K];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  const int R = p.roff[B_COUNT];
+  const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
+  const double HL2PI = 0.9189385332046727;
+  double lq = 0.0, lp = 0.0;
+
+  // ---- reparameterised draw of every real (model_param.py:46-55) + entropy term (:91-92)
+  for (int q = tid; q < R; q += nt) {
+    const int b = block_of(p, q);
+    if (b == B_EPS && !p.model_noisy) continue;
+    const int sz = p.roff[b + 1] - p.roff[b], loc_i = p.toff[b] + (q - p.roff[b]);
+    const double m = theta[loc_i], ls = theta[loc_i + sz];
+    double loc, sc;
+    if (squashed(b)) { loc = 20.0 * sigmoid_d(m) - 10.0; sc = 10.0 * sigmoid_d(ls); }
+    else { loc = m; sc = exp(ls); }
+    const double e = p.noise_mode == CYTOF_NOISE_EXTERNAL ? eps_in[q] : philox_normal_d(p.seed, p.step, (unsigned)q);
+    real[q] = loc + e * sc;
+    eps_out[q] = e;
+    lq += -0.5 * e * e - log(sc) - HL2PI;
+  }
+  __syncthreads();   // single CTA: global writes above are visible block-wide after the barrier
+
+  // ---- transforms, priors, log|det J|, kernel inputs
+  const double* r_d0 = real + p.roff[B_DELTA0];
+  const double* r_d1 = real + p.roff[B_DELTA1];
+  if (tid == 0) {   // delta0 -> mu0 = -cumsum(exp)   (Model.py:223), prior Gamma(a,b)
+    double c = 0.0;
+    for (int l = 0; l < L0; ++l) {
+      const double d = exp(r_d0[l]);
+      c += d;
+      globals[gl.mu0 + l] = (float)(-c);
+      lp += p.delta0_a * log(p.delta0_b) + (p.delta0_a - 1.0) * r_d0[l] - p.delta0_b * d - lgamma(p.delta0_a) + r_d0[l];
+    }
+  }
+  if (tid == 32) {  // delta1 -> mu1 = +cumsum(exp)   (Model.py:227)
+    double c = 0.0;
+    for (int l = 0; l < L1; ++l) {
+      const double d = exp(r_d1[l]);
+      c += d;
+      globals[gl.mu1 + l] = (float)c;
+      lp += p.delta1_a * log(p.delta1_b) + (p.delta1_a - 1.0) * r_d1[l] - p.delta1_b * d - lgamma(p.delta1_a) + r_d1[l];
+    }
+  }
+  if (tid == 64) {  // alpha, v, cumprod(v)  (Model.py:236-239,292-298)
+    const double ra = real[p.roff[B_ALPHA]], alpha = exp(ra);
+    lp += p.alpha_a * log(p.alpha_b) + (p.alpha_a - 1.0) * ra - p.alpha_b * alpha - lgamma(p.alpha_a) + ra;
+    const double conc = p.use_stick_break ? alpha : alpha / (double)K;
+    double cp = 1.0;
+    for (int k = 0; k < K; ++k) {
+      const double rv = real[p.roff[B_V] + k], v = sigmoid_d(rv);
+      lp += (conc - 1.0) * log(v) + log(conc) + log(v) + log1p(-v);
+      cp = p.use_stick_break ? cp * v : v;
+      s_vc[k] = cp;
+    }
+  }
+  for (int i = tid; i < I; i += nt) {  // sig2 -> sig (Model.py:212); eps
+    const double r = real[p.roff[B_SIG2] + i], s2 = exp(r);
+    globals[gl.sig + i] = (float)exp(0.5 * r);
+    if (p.sig2_family == 0)
+      lp += -r - log(p.sig2_p1) - HL2PI - (r - p.sig2_p0) * (r - p.sig2_p0) / (2.0 * p.sig2_p1 * p.sig2_p1) + r;
+    else
+      lp += p.sig2_p0 * log(p.sig2_p1) + (p.sig2_p0 - 1.0) * r - p.sig2_p1 * s2 - lgamma(p.sig2_p0) + r;
+    if (p.model_noisy) {
+      const double re = real[p.roff[B_EPS] + i], e = sigmoid_d(re);
+      globals[gl.eps + i] = (float)e;
+      lp += (p.eps_a - 1.0) * log(e) + (p.eps_b - 1.0) * log1p(-e) + lgamma(p.eps_a + p.eps_b) - lgamma(p.eps_a) -
+            lgamma(p.eps_b) + log(e) + log1p(-e);
+    } else {
+      globals[gl.eps + i] = 0.f;
+    }
+  }
+  {   // eta0 / eta1 / W rows: stick-breaking -> log simplex (model_param.py:62), Dirichlet prior
+    const int rows0 = I * J, rows1 = I * J, rowsW = I;
+    for (int r = tid; r < rows0 + rows1 + rowsW; r += nt) {
+      double logy[CYTOF_MAX_K];
+      int n, goff;
+      const double *x, *conc;
+      if (r < rows0) { n = L0 - 1; x = real + p.roff[B_ETA0] + r * n; conc = p.eta0_c; goff = gl.le0 + r * L0; }
+      else if (r < rows0 + rows1) { const int rr = r - rows0; n = L1 - 1; x = real + p.roff[B_ETA1] + rr * n; conc = p.eta1_c; goff = gl.le1 + rr * L1; }
+      else { const int rr = r - rows0 - rows1; n = K - 1; x = real + p.roff[B_W] + rr * n; conc = p.W_c; goff = gl.lw + rr * K; }
+      lp += stick_row(x, n, logy, nullptr);
+      double csum = 0.0, lg = 0.0;
+      for (int k = 0; k <= n; ++k) {
+        globals[goff + k] = (float)logy[k];
+        lp += (conc[k] - 1.0) * logy[k];
+        csum += conc[k];
+        lg += lgamma(conc[k]);
+      }
+      lp += lgamma(csum) - lg;
+    }
+  }
+  for (int q = tid; q < J * K; q += nt) {   // H: Uniform(0,1) prior contributes 0; log|det J|
+    const double h = sigmoid_d(real[p.roff[B_H] + q]);
+    lp += log(h) + log1p(-h);
+  }
+  for (int q = tid; q < I * J; q += nt) {   // imputation parameters straight into globals
+    globals[gl.vm + q] = (float)theta[p.vae_off + (q / J) * 2 * J + (q % J)];
+    globals[gl.vls + q] = (float)theta[p.vae_off + (q / J) * 2 * J + J + (q % J)];
+  }
+  __syncthreads();
+  for (int j = tid; j < J; j += nt) {       // Z = 1[v > H], thresholded in fp64 (Model.py:33)
+    unsigned long long m = 0ull;
+    for (int k = 0; k < K; ++k)
+      if (s_vc[k] > sigmoid_d(real[p.roff[B_H] + j * K + k])) m |= 1ull << k;
+    zmask[j] = m;
+  }
+  lp = block_sum(lp, sh);
+  lq = block_sum(lq, sh);
+  if (tid == 0) { scalars[0] = lp; scalars[1] = lq; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed: [grad block (BlockLayout, doubles) | ll | log_qy] — already summed over ranks.
+// out_scalars: elbo, ll, lp, lq (lq includes log_qy).  grad_out (may be NULL): d loss / d theta.
+__global__ void __launch_bounds__(1024, 1)
+global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const double* __restrict__ real,
+                       const double* __restrict__ eps, const double* __restrict__ packed,
+                       const double* __restrict__ scalars_in, double* __restrict__ greal,
+                       double* __restrict__ adam_m, double* __restrict__ adam_v, double* __restrict__ grad_out,
+                       double* __restrict__ out_scalars, long long* __restrict__ step_dev, int* __restrict__ flag,
+                       int do_update) {
+  __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K], s_v[CYTOF_MAX_K];
+  __shared__ double sh[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  const int R = p.roff[B_COUNT];
+  const BlockLayout bl = block_layout(I, J, K, L0, L1);
+  const double* __restrict__ G = packed;
+  if (flag && tid == 0) *flag = 0;
+
+  // ---- d(ll + lp)/d real, block by block
+  if (tid == 0) {
+    double suf = 0.0;
+    for (int l = L0 - 1; l >= 0; --l) {       // mu0 = -cumsum(delta0)
+      suf += G[bl.dmu0 + l];
+      const double r = real[p.roff[B_DELTA0] + l], d = exp(r);
+      greal[p.roff[B_DELTA0] + l] = -d * suf + (p.delta0_a - 1.0) - p.delta0_b * d + 1.0;
+    }
+  }
+  if (tid == 32) {
+    double suf = 0.0;
+    for (int l = L1 - 1; l >= 0; --l) {       // mu1 = +cumsum(delta1)
+      suf += G[bl.dmu1 + l];
+      const double r = real[p.roff[B_DELTA1] + l], d = exp(r);
+      greal[p.roff[B_DELTA1] + l] = d * suf + (p.delta1_a - 1.0) - p.delta1_b * d + 1.0;
+    }
+  }
+  if (tid == 64) {   // v, cumprod(v) for the Z chain
+    double cp = 1.0;
+    for (int k = 0; k < K; ++k) {
+      const double v = sigmoid_d(real[p.roff[B_V] + k]);
+      s_v[k] = v;
+      cp = p.use_stick_break ? cp * v : v;
+      s_vc[k] = cp;
+    }
+  }
+  for (int i = tid; i < I; i += nt) {
+    const double r = real[p.roff[B_SIG2] + i];
+    double g = 0.5 * exp(0.5 * r) * G[bl.dsig + i] + 1.0;
+    g += p.sig2_family == 0 ? (-1.0 - (r - p.sig2_p0) / (p.sig2_p1 * p.sig2_p1)) : ((p.sig2_p0 - 1.0) - p.sig2_p1 * exp(r));
+    greal[p.roff[B_SIG2] + i] = g;
+    if (p.model_noisy) {
+      const double e = sigmoid_d(real[p.roff[B_EPS] + i]);
+      greal[p.roff[B_EPS] + i] = e * (1.0 - e) * (G[bl.deps + i] + (p.eps_a - 1.0) / e - (p.eps_b - 1.0) / (1.0 - e)) + (1.0 - 2.0 * e);
+    }
+  }
+  {   // stick-breaking rows: with g_k = dL/dlog y_k (+ Dirichlet (c_k - 1)):
+      //   dL/dx_m = g_m (1 - z_m) - z_m sum_{k>m} g_k + [1 - 2 z_m - z_m (n-1-m)]   (log|det J| part)
+    const int rows0 = I * J, rows1 = I * J, rowsW = I;
+    for (int r = tid; r < rows0 + rows1 + rowsW; r += nt) {
+      double logy[CYTOF_MAX_K], z[CYTOF_MAX_K];
+      int n, go, ro;
+      const double* conc;
+      if (r < rows0) { n = L0 - 1; ro = p.roff[B_ETA0] + r * n; conc = p.eta0_c; go = bl.dle0 + r * L0; }
+      else if (r < rows0 + rows1) { const int rr = r - rows0; n = L1 - 1; ro = p.roff[B_ETA1] + rr * n; conc = p.eta1_c; go = bl.dle1 + rr * L1; }
+      else { const int rr = r - rows0 - rows1; n = K - 1; ro = p.roff[B_W] + rr * n; conc = p.W_c; go = bl.dlw + rr * K; }
+      stick_row(real + ro, n, logy, z);
+      double suf = G[go + n] + conc[n] - 1.0;
+      for (int m = n - 1; m >= 0; --m) {
+        const double gm = G[go + m] + conc[m] - 1.0;
+        greal[ro + m] = gm * (1.0 - z[m]) - z[m] * suf + (1.0 - 2.0 * z[m] - z[m] * (double)(n - 1 - m));
+        suf += gm;
+      }
+    }
+  }
+  __syncthreads();
+  // Z chain (Model.py:22-34): s = sigmoid(x / tau), x = logit(vc_k) - logit(h_jk); dL/dx = G_Z s (1-s) / tau
+  for (int k = tid; k < K; k += nt) s_gvc[k] = 0.0;
+  __syncthreads();
+  for (int k = tid; k < K; k += nt) {       // one thread per feature column: fixed-order sum over j
+    const double vc = s_vc[k], lvc = log(vc) - log1p(-vc);
+    double acc = 0.0;
+    for (int j = 0; j < J; ++j) {
+      const int q = j * K + k;
+      const double h = sigmoid_d(real[p.roff[B_H] + q]);
+      const double s = sigmoid_d((lvc - (log(h) - log1p(-h))) / p.tau);
+      const double a = G[bl.dZ + q] * s * (1.0 - s) / p.tau;
+      greal[p.roff[B_H] + q] = -a + (1.0 - 2.0 * h);
+      acc += a;
+    }
+    s_gvc[k] = acc / (vc * (1.0 - vc));
+  }
+  __syncthreads();
+  if (tid == 0) {   // cumprod backward, v prior Beta(conc, 1), alpha
+    const double ra = real[p.roff[B_ALPHA]], alpha = exp(ra);
+    const double conc = p.use_stick_break ? alpha : alpha / (double)K;
+    double suf = 0.0, dconc = 0.0;
+    for (int m = K - 1; m >= 0; --m) {
+      const double v = s_v[m];
+      double gv;
+      if (p.use_stick_break) { suf += s_gvc[m] * s_vc[m]; gv = suf / v; } else { gv = s_gvc[m]; }
+      greal[p.roff[B_V] + m] = v * (1.0 - v) * (gv + (conc - 1.0) / v) + (1.0 - 2.0 * v);
+      dconc += log(v) + 1.0 / conc;
+    }
+    const double dalpha = p.use_stick_break ? dconc : dconc / (double)K;
+    greal[p.roff[B_ALPHA]] = alpha * dalpha + (p.alpha_a - 1.0) - p.alpha_b * alpha + 1.0;
+  }
+  __syncthreads();
+
+  // ---- chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
+  const long long step = step_dev ? (*step_dev + 1) : p.step_host;
+  const double bc1 = 1.0 - pow(p.beta1, (double)step), bc2s = sqrt(1.0 - pow(p.beta2, (double)step));
+  auto adam = [&](int t, double g, bool scrub) {
+    g *= p.grad_scale;
+    if (scrub && g != g) { g = 0.0; if (flag) *flag = 1; }
+    if (grad_out) grad_out[t] = g;
+    if (!do_update) return;
+    const double mt = adam_m[t] + (1.0 - p.beta1) * (g - adam_m[t]);
+    const double vt = p.beta2 * adam_v[t] + (1.0 - p.beta2) * g * g;
+    adam_m[t] = mt;
+    adam_v[t] = vt;
+    theta[t] -= (p.lr / bc1) * (mt / (sqrt(vt) / bc2s + p.adam_eps));
+  };
+  for (int q = tid; q < R; q += nt) {
+    const int b = block_of(p, q);
+    const int sz = p.roff[b + 1] - p.roff[b], loc_i = p.toff[b] + (q - p.roff[b]);
+    if (b == B_EPS && !p.model_noisy) continue;
+    const double m = theta[loc_i], ls = theta[loc_i + sz], gr = greal[q], e = eps[q];
+    double dloc, dsc, dlogsc;
+    if (squashed(b)) {
+      const double sm = sigmoid_d(m), ss = sigmoid_d(ls);
+      dloc = 20.0 * sm * (1.0 - sm); dsc = 10.0 * ss * (1.0 - ss); dlogsc = 1.0 - ss;
+    } else { dloc = 1.0; dsc = exp(ls); dlogsc = 1.0; }
+    adam(loc_i, gr * dloc, true);                      // d elbo / d m
+    adam(loc_i + sz, gr * e * dsc + dlogsc, true);     // d elbo / d log_s  (+ from -lq)
+  }
+  for (int q = tid; q < I * J; q += nt) {              // imputation parameters (not scrubbed, fit.py:40-45)
+    const int i = q / J, j = q % J;
+    adam(p.vae_off + i * 2 * J + j, G[bl.dvm + q], false);
+    adam(p.vae_off + i * 2 * J + J + j, G[bl.dvls + q] - G[bl.dlq + q], false);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double ll = G[bl.total], lqy = G[bl.total + 1], lp = scalars_in[0], lq = scalars_in[1] + lqy;
+    out_scalars[0] = ll + lp - lq;
+    out_scalars[1] = ll;
+    out_scalars[2] = lp;
+    out_scalars[3] = lq;
+    out_scalars[4] = flag ? (double)*flag : 0.0;
+  }
+  (void)sh;
+}
+
+__global__ void bump_step_kernel(long long* step_dev) { *step_dev += 1; }
+
+// ---------------------------------------------------------------------------------------------
+static void fill_layout(GlobalParams* p) {
+  const int I = p->I, J = p->J, K = p->K, L0 = p->L0, L1 = p->L1;
+  const int sz[B_COUNT] = {L0, L1, p->model_noisy ? I : 0, I, I * J * (L0 - 1), I * J * (L1 - 1), I * (K - 1), 1, K, J * K};
+  int r = 0, t = 0;
+  for (int b = 0; b < B_COUNT; ++b) {
+    p->roff[b] = r;
+    p->toff[b] = t;
+    r += sz[b];
+    t += 2 * sz[b];
+  }
+  p->roff[B_COUNT] = r;
+  p->n_global = t;
+  p->vae_off = t;
+}
+
+int global_make_params(const cytof_global_desc* g, GlobalParams* p) {
+  if (!g) return CYTOF_EINVAL;
+  if (g->I < 1 || g->I > CYTOF_MAX_SAMPLES || g->J < 1 || g->J > CYTOF_MAX_J || g->K < 2 || g->K > CYTOF_MAX_K ||
+      g->L0 < 2 || g->L0 > CYTOF_MAX_L || g->L1 < 2 || g->L1 > CYTOF_MAX_L)
+    return CYTOF_ESHAPE;
+  p->I = g->I; p->J = g->J; p->K = g->K; p->L0 = g->L0; p->L1 = g->L1;
+  p->model_noisy = g->model_noisy; p->use_stick_break = g->use_stick_break;
+  p->noise_mode = g->noise_mode; p->sig2_family = g->sig2_family;
+  p->tau = g->tau;
+  p->delta0_a = g->delta0[0]; p->delta0_b = g->delta0[1];
+  p->delta1_a = g->delta1[0]; p->delta1_b = g->delta1[1];
+  p->sig2_p0 = g->sig2[0]; p->sig2_p1 = g->sig2[1];
+  p->alpha_a = g->alpha[0]; p->alpha_b = g->alpha[1];
+  p->eps_a = g->eps[0]; p->eps_b = g->eps[1];
+  for (int l = 0; l < CYTOF_MAX_L; ++l) { p->eta0_c[l] = g->eta0_conc[l]; p->eta1_c[l] = g->eta1_conc[l]; }
+  for (int k = 0; k < CYTOF_MAX_K; ++k) p->W_c[k] = g->W_conc[k];
+  p->seed = g->seed; p->step = g->step;
+  p->grad_scale = g->grad_scale; p->lr = g->lr; p->beta1 = g->beta1; p->beta2 = g->beta2; p->adam_eps = g->adam_eps;
+  p->step_host = g->adam_step;
+  fill_layout(p);
+  return CYTOF_OK;
+}
+
+int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
+  GlobalParams p;
+  const int rc = global_make_params(g, &p);
+  if (rc != CYTOF_OK) return rc;
+  out[0] = p.roff[B_COUNT];                 // R: number of global reals (= noise length)
+  out[1] = p.n_global;                      // 2R: scrubbed prefix of theta
+  out[2] = p.n_global + 2 * p.I * p.J;      // P: length of theta
+  out[3] = 3 * (int64_t)p.roff[B_COUNT];    // stash doubles: real | eps | greal
+  return CYTOF_OK;
+}
+
+int launch_global_fwd(const cytof_global_desc* g, const double* theta, const double* eps_in, double* stash,
+                      float* globals, uint64_t* zmask, double* scalars, cudaStream_t s, cudaError_t* err) {
+  GlobalParams p;
+  const int rc = global_make_params(g, &p);
+  if (rc != CYTOF_OK) return rc;
+  const int R = p.roff[B_COUNT];
+  global_fwd_kernel<<<1, 1024, 0, s>>>(p, theta, eps_in, stash, stash + R, globals,
+                                       reinterpret_cast<unsigned long long*>(zmask), scalars);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
+}
+
+int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, const double* packed,
+                      const double* scalars_in, double* adam_m, double* adam_v, double* grad_out,
+                      double* out_scalars, int64_t* step_dev, int32_t* flag, int do_update, cudaStream_t s,
+                      cudaError_t* err) {
+  GlobalParams p;
+  const int rc = global_make_params(g, &p);
+  if (rc != CYTOF_OK) return rc;
+  const int R = p.roff[B_COUNT];
+  global_bwd_adam_kernel<<<1, 1024, 0, s>>>(p, theta, stash, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
+                                            adam_v, grad_out, out_scalars, reinterpret_cast<long long*>(step_dev),
+                                            flag, do_update);
+  if (step_dev && do_update) bump_step_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_dev));
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
+}
+
+}  // namespace cytof

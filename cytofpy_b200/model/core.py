@@ -90,6 +90,7 @@ class Model(torch.nn.Module):
         self.dist_group = dist_group
         self._step = 0
         self._prior_cache = {}
+        self._counts_cache = {}
 
         dev, I, J, K, L = self.device, self.I, self.J, self.K, self.L
         ones = lambda n: torch.ones(n, dtype=F64)
@@ -131,9 +132,13 @@ class Model(torch.nn.Module):
         """Per-sample cell counts of the step summed over ranks (for fac_i = N_i / B_i)."""
         if self.dist_group is None:
             return None
-        t = torch.tensor(batch.counts, dtype=torch.int64, device=self.device)
-        torch.distributed.all_reduce(t, group=self.dist_group)
-        return [int(v) for v in t.tolist()]
+        key = tuple(batch.counts)
+        hit = self._counts_cache.get(key)
+        if hit is None:      # counts are static per (minibatch size, shard): one collective, once
+            t = torch.tensor(batch.counts, dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(t, group=self.dist_group)
+            hit = self._counts_cache[key] = [int(v) for v in t.tolist()]
+        return hit
 
     def _make_batch(self, idx):
         counts, idx_dev = self.engine.make_idx(idx)

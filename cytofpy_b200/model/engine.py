@@ -123,6 +123,20 @@ class CellEngine:
         self.launches += 2
         return self.grad_block, self.ll_lqy
 
+    def fwdbwd_packed(self, batch, globals_f32, zmask_i64, packed_f64, counts_global=None):
+        """Same as fwdbwd, results as one fp64 vector [grad block | ll | log_qy] in `packed_f64`."""
+        d = self._desc(batch)
+        self.set_fac(d, batch, counts_global)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.cytof_elbo_fwdbwd_packed(
+                C.byref(d), _ptr(self.y_dev), _ptr(batch.idx), _ptr(batch.eps), _ptr(globals_f32),
+                _ptr(zmask_i64), _ptr(packed_f64), _ptr(self.workspace), C.c_size_t(self.ws_bytes),
+                C.c_void_p(stream))
+        _lib.check(rc)
+        self.launches += 2
+        return packed_f64
+
     def impute(self, batch, globals_f32):
         """Imputed minibatch [C, J] fp32 (reference vae.py:33)."""
         d = self._desc(batch)

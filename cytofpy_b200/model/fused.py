@@ -1,0 +1,157 @@
+"""The whole ADVI step as five kernel launches behind the C ABI:
+
+    [cytof_sample_minibatch x I]  ->  cytof_global_fwd_f64  ->  cytof_elbo_fwdbwd_packed (2 kernels)
+        ->  [NCCL all-reduce of the packed gradient block when cells are sharded]
+        ->  cytof_global_bwd_adam_f64
+
+replacing one reference `update` (fit.py:32-48: Model.forward, backward, NaN scrub, Adam),
+which dispatches ~5,000 ATen ops and syncs the host 4 times.  All variational parameters live
+in ONE flat fp64 device buffer `theta`; the Parameters of `model.mp[key].vp` and of
+`model.y_vae[i]` are re-pointed to views of it, so every reference-style accessor
+(`mod.mp['W'].dist()`, deepcopy snapshots, pickling) keeps working while training runs fused.
+"""
+import ctypes as C
+
+import torch
+from torch.distributions import Beta, Dirichlet, Gamma, Uniform
+from torch.distributions.log_normal import LogNormal
+
+from .. import _lib
+from .engine import Batch, _ptr
+
+F64 = torch.float64
+
+
+def recognise_priors(priors, model_noisy):
+    """Hyper-parameters of the prior families the fused kernels implement, or None if `priors`
+    holds anything else (callers may put arbitrary distributions in the dict, reference
+    sims/cb/cb.py:117-123) — the caller then uses the generic torch path."""
+    f = lambda t: float(torch.as_tensor(t).reshape(-1)[0])
+    out = {}
+    try:
+        for k in ('delta0', 'delta1', 'alpha'):
+            d = priors[k]
+            if not isinstance(d, Gamma):
+                return None
+            out[k] = (f(d.concentration), f(d.rate))
+        d = priors['sig2']
+        if isinstance(d, LogNormal):
+            out['sig2'], out['sig2_family'] = (f(d.loc), f(d.scale)), 0
+        elif isinstance(d, Gamma):
+            out['sig2'], out['sig2_family'] = (f(d.concentration), f(d.rate)), 1
+        else:
+            return None
+        for k in ('eta0', 'eta1', 'W'):
+            d = priors[k]
+            if not isinstance(d, Dirichlet):
+                return None
+            out[k] = [float(v) for v in d.concentration.reshape(-1)]
+        d = priors['H']
+        if not (isinstance(d, Uniform) and f(d.low) == 0.0 and f(d.high) == 1.0):
+            return None
+        if model_noisy:
+            d = priors['eps']
+            if not isinstance(d, Beta):
+                return None
+            out['eps'] = (f(d.concentration1), f(d.concentration0))
+        else:
+            out['eps'] = (1.0, 1.0)
+    except (KeyError, AttributeError):
+        return None
+    return out
+
+
+class FusedStep:
+    def __init__(self, model, lr=1e-1, betas=(0.9, 0.999), adam_eps=1e-8, seed=0):
+        hyp = recognise_priors(model.priors, model.model_noisy)
+        if hyp is None:
+            raise ValueError('priors outside the families the fused global kernels implement')
+        self.model, self.eng, self.dev = model, model.engine, model.device
+        self.lib = _lib.load()
+        I, J, K, L = model.I, model.J, model.K, model.L
+        if len(hyp['eta0']) != L[0] or len(hyp['eta1']) != L[1] or len(hyp['W']) != K:
+            raise ValueError('Dirichlet prior sizes do not match L / K')
+        g = _lib.GlobalDesc()
+        g.I, g.J, g.K, g.L0, g.L1 = I, J, K, L[0], L[1]
+        g.model_noisy, g.use_stick_break = int(model.model_noisy), int(model.use_stick_break)
+        g.noise_mode, g.sig2_family = _lib.NOISE_PHILOX, hyp['sig2_family']
+        g.tau = float(model.tau)
+        for name in ('delta0', 'delta1', 'sig2', 'alpha', 'eps'):
+            getattr(g, name)[0], getattr(g, name)[1] = hyp[name]
+        for i, v in enumerate(hyp['eta0']):
+            g.eta0_conc[i] = v
+        for i, v in enumerate(hyp['eta1']):
+            g.eta1_conc[i] = v
+        for i, v in enumerate(hyp['W']):
+            g.W_conc[i] = v
+        g.seed = int(seed) & (2 ** 64 - 1)
+        g.grad_scale = -1.0 / float(model.Nsum)
+        g.lr, g.beta1, g.beta2, g.adam_eps = float(lr), float(betas[0]), float(betas[1]), float(adam_eps)
+        self.g = g
+        sizes = (C.c_int64 * 4)()
+        _lib.check(self.lib.cytof_global_sizes(C.byref(g), sizes))
+        self.R, self.n_scrub, self.P, stash_len = [int(v) for v in sizes]
+        dev = self.dev
+        z = lambda n, dt=F64: torch.zeros(n, dtype=dt, device=dev)
+        self.theta, self.adam_m, self.adam_v, self.grad = z(self.P), z(self.P), z(self.P), z(self.P)
+        self.stash = z(stash_len)
+        self.packed = z(self.eng.b_off[-1] + 2)
+        self.scalars_in, self.scalars = z(2), z(5)
+        self.globals = z(self.eng.g_off[-1], torch.float32)
+        o = self.eng.g_off
+        self.globals[o[7]:o[8]] = self.eng.b_dev.reshape(-1).to(torch.float32)   # b section: constants
+        self.zmask = z(J, torch.int64)
+        self.flag = z(1, torch.int32)
+        self.step_dev = z(1, torch.int64)
+        self.t = 0
+        self.launches = 0
+        self._bind()
+
+    def _bind(self):
+        """copy the model's current parameters into theta and re-point them to views of it"""
+        m, off = self.model, 0
+        with torch.no_grad():
+            for key in m.mp:
+                vp = m.mp[key].vp
+                n = vp.numel()
+                self.theta[off:off + n] = vp.detach().reshape(-1).to(self.dev)
+                vp.data = self.theta[off:off + n].view(vp.shape)
+                vp.grad = self.grad[off:off + n].view(vp.shape)
+                off += n
+            assert off == self.n_scrub, (off, self.n_scrub)
+            for vae in m.y_vae:
+                for q in (vae.mean, vae.log_sd):
+                    n = q.numel()
+                    self.theta[off:off + n] = q.detach().reshape(-1).to(self.dev)
+                    q.data = self.theta[off:off + n].view(q.shape)
+                    q.grad = self.grad[off:off + n].view(q.shape)
+                    off += n
+            assert off == self.P
+
+    def step(self, idx, global_noise=None, cell_noise=None, update=True):
+        """One fused ELBO forward + backward (+ Adam when update).  idx as for Model.forward.
+        global_noise (R,) / cell_noise (C, J): externally supplied standard normals (parity
+        tests); by default both are drawn in-kernel with Philox keyed by (seed, step).
+        Returns the device tensor [elbo, ll, lp, lq, scrubbed] (no host sync)."""
+        m, eng, g = self.model, self.eng, self.g
+        self.t += 1
+        g.step = self.t
+        g.adam_step = self.t
+        g.noise_mode = _lib.NOISE_EXTERNAL if global_noise is not None else _lib.NOISE_PHILOX
+        counts, idx_dev = eng.make_idx(idx)
+        batch = Batch(counts, idx_dev, cell_noise, step=self.t)
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.cytof_global_fwd_f64(
+                C.byref(g), _ptr(self.theta), _ptr(global_noise), _ptr(self.stash), _ptr(self.globals),
+                _ptr(self.zmask), _ptr(self.scalars_in), stream))
+        eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, m._counts_global(batch))
+        if m.dist_group is not None:
+            torch.distributed.all_reduce(self.packed, group=m.dist_group)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.cytof_global_bwd_adam_f64(
+                C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
+                _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
+                _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
+        self.launches += 4
+        return self.scalars

@@ -9,6 +9,7 @@ import torch
 
 from .. import _lib
 from .core import Model
+from .fused import FusedStep, recognise_priors
 from .priors import default_priors
 
 import ctypes as C
@@ -67,13 +68,16 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         y_mean_init=-3.0, y_sd_init=0.1, trace_every=None, eps_conv=1e-6, tau=0.1,
         backup_every=10, y_quantiles=[0, 35, 70], p_bounds=[.05, .8, .05], scale=1,
         use_stick_break=True, model_noisy=True, init_mp=None, verbose=1, flush=True,
-        K=30, L=None, device=None, sampler='device', noise='philox'):
+        K=30, L=None, device=None, sampler='device', noise='philox', fused=True):
     """reference fit.py:50-147, same arguments and the same returned dict keys
     ('elbo', 'trace', 'mp', 'tau', 'vae', 'use_stick_break', 'y', 'priors', 'model_noisy').
 
     Extras: K / L (used when priors is None — the reference's `priors=None` branch raises
     NameError, fit.py:68-70), device, sampler ('device' = on-GPU keyed permutation,
-    'numpy' = the reference's np.random.choice stream), noise ('philox' | 'external')."""
+    'numpy' = the reference's np.random.choice stream), noise ('philox' | 'external'), fused
+    (True: the whole step runs as 4-5 kernel launches, cytofpy_b200/model/fused.py, when the
+    priors are of the default families; False / other priors: torch autograd + torch Adam
+    around the fused per-cell kernel)."""
     print('scale: {}'.format(scale))
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -94,7 +98,11 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
     if verbose >= 1.1:
         print('state_dict:')
         print(model.state_dict())
-    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    stepper = None
+    if fused and noise == 'philox' and recognise_priors(model.priors, model_noisy) is not None:
+        stepper = FusedStep(model, lr=lr, seed=seed)
+    else:
+        optimizer = torch.optim.Adam(model.parameters(), lr=lr)
     best_mp = copy.deepcopy(model.mp)
     best_vae = copy.deepcopy(model.y_vae)
     elbo_hist, trace = [], []
@@ -104,8 +112,15 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
                    np.random.choice(n, minibatch_size, replace=False) for n in model.N_local]
         else:
             idx = device_minibatch(model, minibatch_size, t, seed)
-        elbo, fixed_grad, ll, lp, lq = update(optimizer, model, idx)
-        elbo_hist.append(elbo.item())
+        if stepper is not None:
+            elbo_t, ll, lp, lq, scrubbed = stepper.step(idx).tolist()     # one 40-byte read-back
+            fixed_grad = scrubbed != 0.0
+            if fixed_grad:
+                print("WARNING: Setting a nan gradient to zero!")
+            elbo_hist.append(elbo_t)
+        else:
+            elbo, fixed_grad, ll, lp, lq = update(optimizer, model, idx)
+            elbo_hist.append(elbo.item())
         elbo_good = not fixed_grad
         if t % print_freq == 0:
             print('{} | {}/{} | elbo: {:.3f} | ll: {:.3f} | lp: {:.3f} | lq: {:.3f}'.format(

@@ -53,6 +53,14 @@ class ModelParam:
         self.size = size
         self.support = support
 
+    def __deepcopy__(self, memo):
+        # snapshots (fit's trace / backup, reference fit.py:122-133) copy only this block even
+        # when vp is a view into the fused step's flat parameter buffer
+        new = ModelParam.__new__(ModelParam)
+        new.vp = torch.nn.Parameter(self.vp.detach().clone())
+        new.size, new.support = self.size, self.support
+        return new
+
     # -- q(real) = Normal(loc, scale); reference model_param.py:46-52
     def loc_scale(self):
         if self.support in ('simplex', 'unit_interval'):

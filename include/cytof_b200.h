@@ -96,6 +96,12 @@ int cytof_elbo_fwdbwd_f32(const cytof_desc* d, const float* y, const int32_t* id
                           const float* globals, const uint64_t* zmask, float* grad_block,
                           double* ll_lqy, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same computation; results as ONE fp64 vector packed[total + 2] = grad block | ll | log_qy
+ * (the buffer a multi-GPU run all-reduces and cytof_global_bwd_adam_f64 consumes). */
+int cytof_elbo_fwdbwd_packed(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                             const float* globals, const uint64_t* zmask, double* packed,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Writes the imputed minibatch y_out[C, J] (vae.py:33) for the same descriptor/noise. */
 int cytof_impute_emit_f32(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                           const float* globals, float* y_out, void* stream);
@@ -119,6 +125,48 @@ int cytof_adam_step_f64(double* param, const double* grad, double* exp_avg, doub
  * key = (seed, step, sample)), O(m) work and no scratch.  m >= N writes 0..N-1 (fit.py:98-99). */
 int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
                            int32_t* idx_out, void* stream);
+
+/* ---- the O(3.5k-scalar) global part of a step as two single-CTA fp64 kernels ----------------
+ * Replaces: model_param.py:46-92 (sample / transform / log|det J| / entropy of every global
+ * block), Model.py:212,223,227,236-243 (sig, mu0, mu1, cumprod(v), Z = 1[v > H] in fp64),
+ * Model.py:289-304 (log prior), their autograd backward, and fit.py:32-48 (loss = -elbo/Nsum,
+ * NaN scrub of the global blocks, Adam).  Priors are the families default_priors uses
+ * (Model.py:92-111): Gamma for delta0/delta1/alpha, LogNormal or Gamma for sig2, Dirichlet for
+ * eta0/eta1/W, Beta for eps, Uniform(0,1) for H, Beta(alpha,1) / Beta(alpha/K,1) for v.
+ *
+ * theta (fp64, device): for each block, in the order delta0 | delta1 | [eps] | sig2 | eta0 | eta1 |
+ * W | alpha | v | H, its m[size] then log_s[size]; then per sample mean[J], log_sd[J]. */
+typedef struct cytof_global_desc {
+  int32_t I, J, K, L0, L1;
+  int32_t model_noisy, use_stick_break;
+  int32_t noise_mode;   /* CYTOF_NOISE_EXTERNAL: eps_in[R] given; CYTOF_NOISE_PHILOX: (seed, step) */
+  int32_t sig2_family;  /* 0 = LogNormal(loc, scale), 1 = Gamma(conc, rate) */
+  int32_t reserved0;
+  double tau;
+  double delta0[2], delta1[2], sig2[2], alpha[2], eps[2]; /* (conc, rate) / (loc, scale) / (a, b) */
+  double eta0_conc[CYTOF_MAX_L], eta1_conc[CYTOF_MAX_L], W_conc[CYTOF_MAX_K];
+  uint64_t seed, step;
+  double grad_scale; /* -1 / Nsum (fit.py:34) */
+  double lr, beta1, beta2, adam_eps;
+  int64_t adam_step; /* 1-based; ignored when step_dev != NULL */
+} cytof_global_desc;
+
+/* out[0] = R (global reals = noise length), out[1] = 2R (scrubbed prefix of theta),
+ * out[2] = P (length of theta), out[3] = stash length in doubles. */
+int cytof_global_sizes(const cytof_global_desc* g, int64_t out[4]);
+
+/* Draw + transform + prior + entropy.  Writes globals (fp32; the b section is left untouched),
+ * zmask[J], scalars[2] = {lp, lq_global} and the stash consumed by the backward call. */
+int cytof_global_fwd_f64(const cytof_global_desc* g, const double* theta, const double* eps_in,
+                         double* stash, float* globals, uint64_t* zmask, double* scalars, void* stream);
+
+/* Backward of the global part from packed (= output of cytof_elbo_fwdbwd_packed, summed over
+ * ranks), loss scaling, NaN scrub (sets *flag), Adam update of theta when do_update != 0.
+ * grad_out (nullable): d loss / d theta.  out_scalars[5] = elbo, ll, lp, lq, scrubbed (0/1). */
+int cytof_global_bwd_adam_f64(const cytof_global_desc* g, double* theta, double* stash,
+                              const double* packed, const double* scalars_in, double* adam_m,
+                              double* adam_v, double* grad_out, double* out_scalars,
+                              int64_t* step_dev, int32_t* flag, int32_t do_update, void* stream);
 
 const char* cytof_strerror(int code);
 const char* cytof_last_cuda_error(void);

@@ -29,9 +29,9 @@ def main():
     dev = torch.device('cuda', 0)
     rng = np.random.default_rng(0)
     g = torch.Generator(device=dev).manual_seed(0)
-    y = torch.randn((I * n, J), device=dev, generator=g) * 2.5
+    y = torch.randn((I * n, J), device=dev, generator=g, dtype=torch.float32) * 2.5
     if a.nan > 0:
-        y[torch.rand((I * n, J), device=dev, generator=g) < a.nan] = float('nan')
+        y[torch.rand((I * n, J), device=dev, generator=g, dtype=torch.float32) < a.nan] = float('nan')
     dirl = lambda al, size: np.log(rng.dirichlet(al, size=size))
     parts = [-np.cumsum(rng.gamma(2, .6, L0)), np.cumsum(rng.gamma(2, .6, L1)), rng.uniform(.5, 1.2, I),
              dirl(np.ones(L0), (I, J)), dirl(np.ones(L1), (I, J)), dirl(np.ones(K), I),
@@ -67,6 +67,11 @@ def main():
     ms = [s.elapsed_time(e) for s, e in ev[3:]]
     cells = batch.ncells
     med = statistics.median(ms)
+    blk = eng.grad_block.cpu().numpy()
+    if not np.isfinite(blk).all() or not np.isfinite(eng.ll_lqy.cpu().numpy()).all():
+        names = ['dmu0', 'dmu1', 'dsig', 'dle0', 'dle1', 'dlw', 'dZ', 'deps', 'dvm', 'dvls', 'dlq']
+        bad = [nm for nm, a, b in zip(names, eng.b_off[:-1], eng.b_off[1:]) if not np.isfinite(blk[a:b]).all()]
+        print('NON-FINITE sections:', bad, 'll_lqy', eng.ll_lqy.tolist())
     print('%s lib=%s cells=%d  median %.4f ms  min %.4f ms  %.3f Gcells/s  ll=%.6e' % (
         a.workload, os.path.basename(os.environ.get('CYTOF_B200_LIB', 'default')), cells, med, min(ms),
         cells / med / 1e6, eng.ll_lqy[0].item()))
