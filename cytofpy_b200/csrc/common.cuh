@@ -7,7 +7,10 @@
 
 namespace cytof {
 
-constexpr int kThreads = 256;             // 8 warps per CTA
+#ifndef CYTOF_THREADS
+#define CYTOF_THREADS 256
+#endif
+constexpr int kThreads = CYTOF_THREADS;   // warps per CTA = kThreads / 32
 constexpr int kWarps = kThreads / 32;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

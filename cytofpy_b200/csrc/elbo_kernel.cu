@@ -18,6 +18,7 @@
 // the finalise kernel sums the per-CTA records in fp64 in a fixed order => bitwise
 // reproducible results for a given grid.
 #include "common.cuh"
+#include "elbo_kernel_j32.cuh"
 
 namespace cytof {
 
@@ -542,14 +543,27 @@ using KernelFn = void (*)(const ElboParams);
 
 struct Variant {
   int lm0, lm1, jp, kp;
-  KernelFn fn[2];  // [noisy]
+  int smem_floats_per_warp, smem_floats_extra;
+  KernelFn fn[4];  // [noisy + 2 * has_idx]
 };
 #define CYTOF_VARIANT(a, b, jp, kp) \
-  { a, b, jp, kp, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true> } }
+  { a, b, jp, kp, (jp) * 32 + (kp) * 32, 0, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
+                                           elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true> } }
+#define CYTOF_VARIANT_J32(a, b) \
+  { a, b, 1, 1, kCPW * 64, kJ32ConstFloats, { elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
+                             elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true> } }
+#ifndef CYTOF_J32
+#define CYTOF_J32 1   // 1: packed-fp32, two-cells-in-flight kernel for J,K <= 32; 0: first kernel
+#endif
 // ordered by cost: the first variant that fits is used; (8,8) is the padded fallback
 static const Variant kVariants[] = {
+#if CYTOF_J32
+    CYTOF_VARIANT_J32(3, 3), CYTOF_VARIANT_J32(4, 3), CYTOF_VARIANT_J32(5, 3),
+    CYTOF_VARIANT_J32(5, 5), CYTOF_VARIANT_J32(8, 8),
+#else
     CYTOF_VARIANT(3, 3, 1, 1), CYTOF_VARIANT(4, 3, 1, 1), CYTOF_VARIANT(5, 3, 1, 1),
     CYTOF_VARIANT(5, 5, 1, 1), CYTOF_VARIANT(8, 8, 1, 1),
+#endif
     CYTOF_VARIANT(3, 3, 2, 2), CYTOF_VARIANT(5, 5, 2, 2), CYTOF_VARIANT(8, 8, 2, 2),
 };
 
@@ -563,7 +577,7 @@ static const Variant* pick_variant(int J, int K, int L0, int L1) {
 
 static size_t fused_smem_bytes(const Variant* v, int J, int K, int L0, int L1) {
   const PartialLayout pl = partial_layout(J, K, L0, L1);
-  return sizeof(float) * (size_t)(kWarps * (v->jp * 32 + v->kp * 32) + pl.total);
+  return sizeof(float) * (size_t)(kWarps * v->smem_floats_per_warp + v->smem_floats_extra + pl.total);
 }
 
 static int g_sm_count[64] = {0};
@@ -578,13 +592,13 @@ static int device_sm_count() {
   return g_sm_count[dev];
 }
 
-constexpr int kMaxCtasPerSm = 4;   // upper bound used to size the workspace
+constexpr int kMaxCtasPerSm = 8;   // upper bound used to size the workspace
 constexpr int kMinCellsPerWarp = 4;
 
 int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAMPLES; }
 
 // resident CTAs per SM of one kernel variant (cached; immutable per device + binary)
-static int g_occ[64][16][2] = {};
+static int g_occ[64][16][4] = {};
 static int variant_occupancy(const Variant* v, int noisy, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
@@ -682,13 +696,14 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15;
   p.partials = reinterpret_cast<float*>(wp);
   const size_t smem = fused_smem_bytes(v, d->J, d->K, d->L0, d->L1);
-  const int nblocks = plan_grid(d, &p, variant_occupancy(v, d->model_noisy ? 1 : 0, smem));
+  const int fi = (d->model_noisy ? 1 : 0) + (idx ? 2 : 0);
+  const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem));
   const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
   const size_t need = sizeof(float) * (size_t)pl.total * (size_t)nblocks + (wp - reinterpret_cast<uintptr_t>(workspace));
   if (need > workspace_bytes_) return CYTOF_EWORKSPACE;
   const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
   if (nblocks > 0) {
-    KernelFn fn = v->fn[d->model_noisy ? 1 : 0];
+    KernelFn fn = v->fn[fi];
     if (smem > 48 * 1024) {
       *err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (*err != cudaSuccess) return CYTOF_ECUDA;
