@@ -67,6 +67,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ready = threading.Event()       # NVML is initialised before the timed region starts
 
     def run(self):
         try:
@@ -76,15 +77,17 @@ class ClockSampler(threading.Thread):
             phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
             h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ready.set()
             while not self.stop_flag:
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.001)
         except Exception as e:  # NVML missing: report it, do not fake numbers
             self.reasons.add('nvml_unavailable:%s' % type(e).__name__)
+        self.ready.set()
 
     def summary(self):
         return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
@@ -184,6 +187,8 @@ def run_ours(args, w, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(10.0)
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = fs.launches
     for t in range(args.steps):

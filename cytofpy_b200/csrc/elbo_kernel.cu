@@ -450,15 +450,33 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   if (t >= bl.total + 2) return;
   const float* __restrict__ P = p.partials;
   const float* __restrict__ G = p.globals;
-  auto sum_sample = [&](int i, int off) -> double {
+  auto sum_range = [&](int b0, int b1, int off) -> double {
+    // 8 independent loads in flight per thread; the summation ORDER stays fixed (reproducible)
     double a = 0.0;
-    for (int b = p.blk_begin[i]; b < p.blk_begin[i + 1]; ++b) a += (double)P[(size_t)b * pl.total + off];
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(P + (size_t)(b + u) * pl.total + off);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += (double)v[u];
+    }
+    for (; b < b1; ++b) a += (double)__ldg(P + (size_t)b * pl.total + off);
     return a;
   };
+  auto sum_sample = [&](int i, int off) -> double { return sum_range(p.blk_begin[i], p.blk_begin[i + 1], off); };
   if (t >= bl.total) {  // ll, log_qy
     const int which = t - bl.total;
     double a = 0.0;
-    for (int b = 0; b < p.nblocks; ++b)
+    int b = 0;
+    for (; b + 8 <= p.nblocks; b += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = reinterpret_cast<const double*>(P + (size_t)(b + u) * pl.total + pl.dbl)[which];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; b < p.nblocks; ++b)
       a += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
     if (ll_lqy) ll_lqy[which] = a;
     if (packed) packed[t] = a;
@@ -492,8 +510,7 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     r = sum_sample(i, pl.gW + k);
   } else if (t < bl.deps) {  // dZ_jk = ln2 * sum g_k D2_j   (D2 in log2 units)
     const int q = t - bl.dZ, j = q / K, k = q % K;
-    for (int i = 0; i < I; ++i) r += sum_sample(i, pl.dZ + k * J + j);
-    r *= 0.6931471805599453;
+    r = sum_range(0, p.nblocks, pl.dZ + k * J + j) * 0.6931471805599453;
   } else if (t < bl.dvm) {  // deps_i = -sum fac rho/(1-eps) + sum fac (1-rho)/eps
     const int i = t - bl.deps;
     const double e = (double)G[gl.eps + i];

@@ -72,28 +72,25 @@ __device__ double block_sum(double v, double* sh) {
   return t;
 }
 
-// stick-breaking of one row x[0..n) -> log y[0..n]  (torch StickBreakingTransform incl. its
-// clipped sigmoid); returns log|det J| of the row
-__device__ double stick_row(const double* x, int n, double* logy, double* zbuf) {
-  const double tiny = 2.2250738585072014e-308, one_m_eps = 1.0 - 2.220446049250313e-16;
-  double acc = 0.0, ld = 0.0;
-  for (int k = 0; k < n; ++k) {
-    double z = sigmoid_d(x[k] - log((double)(n - k)));
-    z = fmin(fmax(z, tiny), one_m_eps);
-    if (zbuf) zbuf[k] = z;
-    const double l1mz = log1p(-z);
-    logy[k] = log(z) + acc;
-    ld += l1mz + logy[k];
-    acc += l1mz;
-  }
-  logy[n] = acc;
-  return ld;
+// Which stick-breaking row family a real belongs to: n = row length, k = position in the row.
+struct RowPos { int n, k; };
+__device__ __forceinline__ RowPos row_pos(const GlobalParams& p, int b, int local) {
+  const int n = b == B_ETA0 ? p.L0 - 1 : (b == B_ETA1 ? p.L1 - 1 : p.K - 1);
+  return RowPos{n, local % n};
 }
 
 // ---------------------------------------------------------------------------------------------
+// Structure of both kernels: (1) an element-parallel phase that evaluates every fp64
+// transcendental (exp / log / sigmoid, ~10^2 cycles each) with one thread per scalar, then
+// (2) short serial scans (cumsum, cumprod, stick-breaking prefix sums) that only add and
+// multiply.  aux1 / aux2 carry the per-element results between the phases and to the backward.
+//   eta0 / eta1 / W element:  aux1 = log z,   aux2 = log(1 - z)   (z = clipped sigmoid)
+//   H element:                aux1 = h                            v element: aux1 = v, aux2 = log v
+//   delta element:            aux1 = exp(real)
 __global__ void __launch_bounds__(1024, 1)
 global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const double* __restrict__ eps_in,
-                  double* __restrict__ real, double* __restrict__ eps_out, float* __restrict__ globals,
+                  double* __restrict__ real, double* __restrict__ eps_out, double* __restrict__ aux1,
+                  double* __restrict__ aux2, float* __restrict__ globals,
                   unsigned long long* __restrict__ zmask, double* __restrict__ scalars /* lp, lq_global */) {
   __shared__ double sh[32];
   __shared__ double s_vc[CYTOF_MAX_K];
@@ -102,106 +99,123 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
   const int R = p.roff[B_COUNT];
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
   const double HL2PI = 0.9189385332046727;
+  const double tiny = 2.2250738585072014e-308, one_m_eps = 1.0 - 2.220446049250313e-16;
   double lq = 0.0, lp = 0.0;
 
-  // ---- reparameterised draw of every real (model_param.py:46-55) + entropy term (:91-92)
+  // ---- (1) element-parallel: reparameterised draw (model_param.py:46-55), entropy term
+  //      (:91-92), element-wise transforms and the element-wise parts of prior + log|det J|
   for (int q = tid; q < R; q += nt) {
     const int b = block_of(p, q);
-    if (b == B_EPS && !p.model_noisy) continue;
-    const int sz = p.roff[b + 1] - p.roff[b], loc_i = p.toff[b] + (q - p.roff[b]);
+    const int sz = p.roff[b + 1] - p.roff[b], local = q - p.roff[b], loc_i = p.toff[b] + local;
     const double m = theta[loc_i], ls = theta[loc_i + sz];
     double loc, sc;
     if (squashed(b)) { loc = 20.0 * sigmoid_d(m) - 10.0; sc = 10.0 * sigmoid_d(ls); }
     else { loc = m; sc = exp(ls); }
     const double e = p.noise_mode == CYTOF_NOISE_EXTERNAL ? eps_in[q] : philox_normal_d(p.seed, p.step, (unsigned)q);
-    real[q] = loc + e * sc;
+    const double r = loc + e * sc;
+    real[q] = r;
     eps_out[q] = e;
     lq += -0.5 * e * e - log(sc) - HL2PI;
-  }
-  __syncthreads();   // single CTA: global writes above are visible block-wide after the barrier
-
-  // ---- transforms, priors, log|det J|, kernel inputs
-  const double* r_d0 = real + p.roff[B_DELTA0];
-  const double* r_d1 = real + p.roff[B_DELTA1];
-  if (tid == 0) {   // delta0 -> mu0 = -cumsum(exp)   (Model.py:223), prior Gamma(a,b)
-    double c = 0.0;
-    for (int l = 0; l < L0; ++l) {
-      const double d = exp(r_d0[l]);
-      c += d;
-      globals[gl.mu0 + l] = (float)(-c);
-      lp += p.delta0_a * log(p.delta0_b) + (p.delta0_a - 1.0) * r_d0[l] - p.delta0_b * d - lgamma(p.delta0_a) + r_d0[l];
-    }
-  }
-  if (tid == 32) {  // delta1 -> mu1 = +cumsum(exp)   (Model.py:227)
-    double c = 0.0;
-    for (int l = 0; l < L1; ++l) {
-      const double d = exp(r_d1[l]);
-      c += d;
-      globals[gl.mu1 + l] = (float)c;
-      lp += p.delta1_a * log(p.delta1_b) + (p.delta1_a - 1.0) * r_d1[l] - p.delta1_b * d - lgamma(p.delta1_a) + r_d1[l];
-    }
-  }
-  if (tid == 64) {  // alpha, v, cumprod(v)  (Model.py:236-239,292-298)
-    const double ra = real[p.roff[B_ALPHA]], alpha = exp(ra);
-    lp += p.alpha_a * log(p.alpha_b) + (p.alpha_a - 1.0) * ra - p.alpha_b * alpha - lgamma(p.alpha_a) + ra;
-    const double conc = p.use_stick_break ? alpha : alpha / (double)K;
-    double cp = 1.0;
-    for (int k = 0; k < K; ++k) {
-      const double rv = real[p.roff[B_V] + k], v = sigmoid_d(rv);
-      lp += (conc - 1.0) * log(v) + log(conc) + log(v) + log1p(-v);
-      cp = p.use_stick_break ? cp * v : v;
-      s_vc[k] = cp;
-    }
-  }
-  for (int i = tid; i < I; i += nt) {  // sig2 -> sig (Model.py:212); eps
-    const double r = real[p.roff[B_SIG2] + i], s2 = exp(r);
-    globals[gl.sig + i] = (float)exp(0.5 * r);
-    if (p.sig2_family == 0)
-      lp += -r - log(p.sig2_p1) - HL2PI - (r - p.sig2_p0) * (r - p.sig2_p0) / (2.0 * p.sig2_p1 * p.sig2_p1) + r;
-    else
-      lp += p.sig2_p0 * log(p.sig2_p1) + (p.sig2_p0 - 1.0) * r - p.sig2_p1 * s2 - lgamma(p.sig2_p0) + r;
-    if (p.model_noisy) {
-      const double re = real[p.roff[B_EPS] + i], e = sigmoid_d(re);
-      globals[gl.eps + i] = (float)e;
-      lp += (p.eps_a - 1.0) * log(e) + (p.eps_b - 1.0) * log1p(-e) + lgamma(p.eps_a + p.eps_b) - lgamma(p.eps_a) -
-            lgamma(p.eps_b) + log(e) + log1p(-e);
-    } else {
-      globals[gl.eps + i] = 0.f;
-    }
-  }
-  {   // eta0 / eta1 / W rows: stick-breaking -> log simplex (model_param.py:62), Dirichlet prior
-    const int rows0 = I * J, rows1 = I * J, rowsW = I;
-    for (int r = tid; r < rows0 + rows1 + rowsW; r += nt) {
-      double logy[CYTOF_MAX_K];
-      int n, goff;
-      const double *x, *conc;
-      if (r < rows0) { n = L0 - 1; x = real + p.roff[B_ETA0] + r * n; conc = p.eta0_c; goff = gl.le0 + r * L0; }
-      else if (r < rows0 + rows1) { const int rr = r - rows0; n = L1 - 1; x = real + p.roff[B_ETA1] + rr * n; conc = p.eta1_c; goff = gl.le1 + rr * L1; }
-      else { const int rr = r - rows0 - rows1; n = K - 1; x = real + p.roff[B_W] + rr * n; conc = p.W_c; goff = gl.lw + rr * K; }
-      lp += stick_row(x, n, logy, nullptr);
-      double csum = 0.0, lg = 0.0;
-      for (int k = 0; k <= n; ++k) {
-        globals[goff + k] = (float)logy[k];
-        lp += (conc[k] - 1.0) * logy[k];
-        csum += conc[k];
-        lg += lgamma(conc[k]);
+    switch (b) {
+      case B_DELTA0: case B_DELTA1: {
+        const double d = exp(r), a_ = b == B_DELTA0 ? p.delta0_a : p.delta1_a, b_ = b == B_DELTA0 ? p.delta0_b : p.delta1_b;
+        aux1[q] = d;
+        lp += a_ * log(b_) + (a_ - 1.0) * r - b_ * d - lgamma(a_) + r;
+      } break;
+      case B_EPS: {
+        const double ee = sigmoid_d(r);
+        globals[gl.eps + local] = (float)ee;
+        lp += (p.eps_a - 1.0) * log(ee) + (p.eps_b - 1.0) * log1p(-ee) + lgamma(p.eps_a + p.eps_b) - lgamma(p.eps_a) -
+              lgamma(p.eps_b) + log(ee) + log1p(-ee);
+      } break;
+      case B_SIG2: {
+        globals[gl.sig + local] = (float)exp(0.5 * r);
+        if (p.sig2_family == 0)
+          lp += -r - log(p.sig2_p1) - HL2PI - (r - p.sig2_p0) * (r - p.sig2_p0) / (2.0 * p.sig2_p1 * p.sig2_p1) + r;
+        else
+          lp += p.sig2_p0 * log(p.sig2_p1) + (p.sig2_p0 - 1.0) * r - p.sig2_p1 * exp(r) - lgamma(p.sig2_p0) + r;
+      } break;
+      case B_ETA0: case B_ETA1: case B_W: {
+        const RowPos rp = row_pos(p, b, local);
+        double z = sigmoid_d(r - log((double)(rp.n - rp.k)));
+        z = fmin(fmax(z, tiny), one_m_eps);
+        aux1[q] = log(z);
+        aux2[q] = log1p(-z);
+      } break;
+      case B_ALPHA: {
+        const double alpha = exp(r);
+        aux1[q] = alpha;
+        lp += p.alpha_a * log(p.alpha_b) + (p.alpha_a - 1.0) * r - p.alpha_b * alpha - lgamma(p.alpha_a) + r;
+      } break;
+      case B_V: {
+        const double v = sigmoid_d(r), lv = log(v);
+        aux1[q] = v;
+        aux2[q] = lv;
+        lp += lv + log1p(-v);          // log|det J|; the Beta(conc, 1) part needs alpha: phase 2
+      } break;
+      default: {                        // B_H: Uniform(0,1) prior contributes 0
+        const double h = sigmoid_d(r);
+        aux1[q] = h;
+        lp += log(h) + log1p(-h);
       }
-      lp += lgamma(csum) - lg;
     }
   }
-  for (int q = tid; q < J * K; q += nt) {   // H: Uniform(0,1) prior contributes 0; log|det J|
-    const double h = sigmoid_d(real[p.roff[B_H] + q]);
-    lp += log(h) + log1p(-h);
-  }
+  if (!p.model_noisy)
+    for (int i = tid; i < I; i += nt) globals[gl.eps + i] = 0.f;
   for (int q = tid; q < I * J; q += nt) {   // imputation parameters straight into globals
     globals[gl.vm + q] = (float)theta[p.vae_off + (q / J) * 2 * J + (q % J)];
     globals[gl.vls + q] = (float)theta[p.vae_off + (q / J) * 2 * J + J + (q % J)];
+  }
+  __syncthreads();   // single CTA: the global writes above are visible block-wide after the barrier
+
+  // ---- (2) serial scans (adds / multiplies only)
+  if (tid == 0) {   // mu0 = -cumsum(delta0)   (Model.py:223)
+    double c = 0.0;
+    for (int l = 0; l < L0; ++l) { c += aux1[p.roff[B_DELTA0] + l]; globals[gl.mu0 + l] = (float)(-c); }
+  }
+  if (tid == 32) {  // mu1 = +cumsum(delta1)   (Model.py:227)
+    double c = 0.0;
+    for (int l = 0; l < L1; ++l) { c += aux1[p.roff[B_DELTA1] + l]; globals[gl.mu1 + l] = (float)c; }
+  }
+  if (tid == 64) {  // v prior Beta(conc, 1) and cumprod(v)  (Model.py:236-239,292-298)
+    const double alpha = aux1[p.roff[B_ALPHA]];
+    const double conc = p.use_stick_break ? alpha : alpha / (double)K;
+    double cp = 1.0, slv = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double v = aux1[p.roff[B_V] + k];
+      slv += aux2[p.roff[B_V] + k];
+      cp = p.use_stick_break ? cp * v : v;
+      s_vc[k] = cp;
+    }
+    lp += (conc - 1.0) * slv + (double)K * log(conc);
+  }
+  {   // eta0 / eta1 / W rows: log y_k = log z_k + sum_{m<k} log(1-z_m); Dirichlet prior; log|det J|
+    const int rows0 = I * J, rows1 = I * J, rowsW = I;
+    for (int rr0 = tid - 96; rr0 < rows0 + rows1 + rowsW; rr0 += nt) {   // threads 96.. : keep the scan warps free
+      if (rr0 < 0) continue;
+      int n, goff, ro;
+      const double* conc;
+      if (rr0 < rows0) { n = L0 - 1; ro = p.roff[B_ETA0] + rr0 * n; conc = p.eta0_c; goff = gl.le0 + rr0 * L0; }
+      else if (rr0 < rows0 + rows1) { const int rr = rr0 - rows0; n = L1 - 1; ro = p.roff[B_ETA1] + rr * n; conc = p.eta1_c; goff = gl.le1 + rr * L1; }
+      else { const int rr = rr0 - rows0 - rows1; n = K - 1; ro = p.roff[B_W] + rr * n; conc = p.W_c; goff = gl.lw + rr * K; }
+      double acc = 0.0, csum = 0.0, lg = 0.0;
+      for (int k = 0; k < n; ++k) {
+        const double ly = aux1[ro + k] + acc;
+        globals[goff + k] = (float)ly;
+        lp += (conc[k] - 1.0) * ly + aux2[ro + k] + ly;
+        acc += aux2[ro + k];
+        csum += conc[k];
+        lg += lgamma(conc[k]);
+      }
+      globals[goff + n] = (float)acc;
+      lp += (conc[n] - 1.0) * acc + lgamma(csum + conc[n]) - lg - lgamma(conc[n]);
+    }
   }
   __syncthreads();
   for (int j = tid; j < J; j += nt) {       // Z = 1[v > H], thresholded in fp64 (Model.py:33)
     unsigned long long m = 0ull;
     for (int k = 0; k < K; ++k)
-      if (s_vc[k] > sigmoid_d(real[p.roff[B_H] + j * K + k])) m |= 1ull << k;
+      if (s_vc[k] > aux1[p.roff[B_H] + j * K + k]) m |= 1ull << k;
     zmask[j] = m;
   }
   lp = block_sum(lp, sh);
@@ -211,16 +225,15 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
 
 // ---------------------------------------------------------------------------------------------
 // packed: [grad block (BlockLayout, doubles) | ll | log_qy] — already summed over ranks.
-// out_scalars: elbo, ll, lp, lq (lq includes log_qy).  grad_out (may be NULL): d loss / d theta.
+// out_scalars: elbo, ll, lp, lq (lq includes log_qy), scrubbed.  grad_out (may be NULL): d loss / d theta.
 __global__ void __launch_bounds__(1024, 1)
 global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const double* __restrict__ real,
-                       const double* __restrict__ eps, const double* __restrict__ packed,
-                       const double* __restrict__ scalars_in, double* __restrict__ greal,
-                       double* __restrict__ adam_m, double* __restrict__ adam_v, double* __restrict__ grad_out,
-                       double* __restrict__ out_scalars, long long* __restrict__ step_dev, int* __restrict__ flag,
-                       int do_update) {
-  __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K], s_v[CYTOF_MAX_K];
-  __shared__ double sh[32];
+                       const double* __restrict__ eps, const double* __restrict__ aux1, double* __restrict__ aux2,
+                       const double* __restrict__ packed, const double* __restrict__ scalars_in,
+                       double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
+                       double* __restrict__ grad_out, double* __restrict__ out_scalars,
+                       long long* __restrict__ step_dev, int* __restrict__ flag, int do_update) {
+  __shared__ double s_vc[CYTOF_MAX_K], s_lvc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
@@ -228,12 +241,54 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
   const double* __restrict__ G = packed;
   if (flag && tid == 0) *flag = 0;
 
-  // ---- d(ll + lp)/d real, block by block
+  // ---- (0) cumprod(v) and logit of it (K values)
+  if (tid == 0) {
+    double cp = 1.0;
+    for (int k = 0; k < K; ++k) { cp = p.use_stick_break ? cp * aux1[p.roff[B_V] + k] : aux1[p.roff[B_V] + k]; s_vc[k] = cp; }
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += nt) s_lvc[k] = log(s_vc[k]) - log1p(-s_vc[k]);
+  __syncthreads();
+
+  // ---- (1) element-parallel part of d(ll + lp)/d real
+  for (int q = tid; q < R; q += nt) {
+    const int b = block_of(p, q);
+    const int local = q - p.roff[b];
+    const double r = real[q];
+    switch (b) {
+      case B_SIG2: {
+        double g = 0.5 * exp(0.5 * r) * G[bl.dsig + local] + 1.0;
+        g += p.sig2_family == 0 ? (-1.0 - (r - p.sig2_p0) / (p.sig2_p1 * p.sig2_p1)) : ((p.sig2_p0 - 1.0) - p.sig2_p1 * exp(r));
+        greal[q] = g;
+      } break;
+      case B_EPS: {
+        const double e = sigmoid_d(r);
+        greal[q] = e * (1.0 - e) * (G[bl.deps + local] + (p.eps_a - 1.0) / e - (p.eps_b - 1.0) / (1.0 - e)) + (1.0 - 2.0 * e);
+      } break;
+      case B_ETA0: case B_ETA1: case B_W:
+        aux2[q] = exp(aux1[q]);          // z itself, for the row scans below
+        break;
+      case B_H: {
+        // Z chain (Model.py:22-34): s = sigmoid(x / tau), x = logit(vc_k) - logit(h_jk);
+        // dL/dx = G_Z s (1-s) / tau;  d x / d real_H = -1
+        const int k = local % K;
+        const double h = aux1[q];
+        const double s = sigmoid_d((s_lvc[k] - (log(h) - log1p(-h))) / p.tau);
+        const double a = G[bl.dZ + local] * s * (1.0 - s) / p.tau;
+        aux2[q] = a;
+        greal[q] = -a + (1.0 - 2.0 * h);
+      } break;
+      default: break;                    // delta0 / delta1 / alpha / v: scans below
+    }
+  }
+  __syncthreads();
+
+  // ---- (2) serial scans
   if (tid == 0) {
     double suf = 0.0;
     for (int l = L0 - 1; l >= 0; --l) {       // mu0 = -cumsum(delta0)
       suf += G[bl.dmu0 + l];
-      const double r = real[p.roff[B_DELTA0] + l], d = exp(r);
+      const double d = aux1[p.roff[B_DELTA0] + l];
       greal[p.roff[B_DELTA0] + l] = -d * suf + (p.delta0_a - 1.0) - p.delta0_b * d + 1.0;
     }
   }
@@ -241,83 +296,52 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
     double suf = 0.0;
     for (int l = L1 - 1; l >= 0; --l) {       // mu1 = +cumsum(delta1)
       suf += G[bl.dmu1 + l];
-      const double r = real[p.roff[B_DELTA1] + l], d = exp(r);
+      const double d = aux1[p.roff[B_DELTA1] + l];
       greal[p.roff[B_DELTA1] + l] = d * suf + (p.delta1_a - 1.0) - p.delta1_b * d + 1.0;
     }
   }
-  if (tid == 64) {   // v, cumprod(v) for the Z chain
-    double cp = 1.0;
-    for (int k = 0; k < K; ++k) {
-      const double v = sigmoid_d(real[p.roff[B_V] + k]);
-      s_v[k] = v;
-      cp = p.use_stick_break ? cp * v : v;
-      s_vc[k] = cp;
-    }
-  }
-  for (int i = tid; i < I; i += nt) {
-    const double r = real[p.roff[B_SIG2] + i];
-    double g = 0.5 * exp(0.5 * r) * G[bl.dsig + i] + 1.0;
-    g += p.sig2_family == 0 ? (-1.0 - (r - p.sig2_p0) / (p.sig2_p1 * p.sig2_p1)) : ((p.sig2_p0 - 1.0) - p.sig2_p1 * exp(r));
-    greal[p.roff[B_SIG2] + i] = g;
-    if (p.model_noisy) {
-      const double e = sigmoid_d(real[p.roff[B_EPS] + i]);
-      greal[p.roff[B_EPS] + i] = e * (1.0 - e) * (G[bl.deps + i] + (p.eps_a - 1.0) / e - (p.eps_b - 1.0) / (1.0 - e)) + (1.0 - 2.0 * e);
-    }
+  for (int k = tid - 64; k >= 0 && k < K; k += nt) {   // column sums of dL/dx over j (threads 64..64+K)
+    double acc = 0.0;
+    for (int j = 0; j < J; ++j) acc += aux2[p.roff[B_H] + j * K + k];
+    s_gvc[k] = acc / (s_vc[k] * (1.0 - s_vc[k]));
   }
   {   // stick-breaking rows: with g_k = dL/dlog y_k (+ Dirichlet (c_k - 1)):
       //   dL/dx_m = g_m (1 - z_m) - z_m sum_{k>m} g_k + [1 - 2 z_m - z_m (n-1-m)]   (log|det J| part)
     const int rows0 = I * J, rows1 = I * J, rowsW = I;
-    for (int r = tid; r < rows0 + rows1 + rowsW; r += nt) {
-      double logy[CYTOF_MAX_K], z[CYTOF_MAX_K];
+    for (int rr0 = tid - 128; rr0 < rows0 + rows1 + rowsW; rr0 += nt) {   // threads 128.. : keep the scan warps free
+      if (rr0 < 0) continue;
       int n, go, ro;
       const double* conc;
-      if (r < rows0) { n = L0 - 1; ro = p.roff[B_ETA0] + r * n; conc = p.eta0_c; go = bl.dle0 + r * L0; }
-      else if (r < rows0 + rows1) { const int rr = r - rows0; n = L1 - 1; ro = p.roff[B_ETA1] + rr * n; conc = p.eta1_c; go = bl.dle1 + rr * L1; }
-      else { const int rr = r - rows0 - rows1; n = K - 1; ro = p.roff[B_W] + rr * n; conc = p.W_c; go = bl.dlw + rr * K; }
-      stick_row(real + ro, n, logy, z);
+      if (rr0 < rows0) { n = L0 - 1; ro = p.roff[B_ETA0] + rr0 * n; conc = p.eta0_c; go = bl.dle0 + rr0 * L0; }
+      else if (rr0 < rows0 + rows1) { const int rr = rr0 - rows0; n = L1 - 1; ro = p.roff[B_ETA1] + rr * n; conc = p.eta1_c; go = bl.dle1 + rr * L1; }
+      else { const int rr = rr0 - rows0 - rows1; n = K - 1; ro = p.roff[B_W] + rr * n; conc = p.W_c; go = bl.dlw + rr * K; }
       double suf = G[go + n] + conc[n] - 1.0;
       for (int m = n - 1; m >= 0; --m) {
-        const double gm = G[go + m] + conc[m] - 1.0;
-        greal[ro + m] = gm * (1.0 - z[m]) - z[m] * suf + (1.0 - 2.0 * z[m] - z[m] * (double)(n - 1 - m));
+        const double gm = G[go + m] + conc[m] - 1.0, z = aux2[ro + m];
+        greal[ro + m] = gm * (1.0 - z) - z * suf + (1.0 - 2.0 * z - z * (double)(n - 1 - m));
         suf += gm;
       }
     }
   }
   __syncthreads();
-  // Z chain (Model.py:22-34): s = sigmoid(x / tau), x = logit(vc_k) - logit(h_jk); dL/dx = G_Z s (1-s) / tau
-  for (int k = tid; k < K; k += nt) s_gvc[k] = 0.0;
-  __syncthreads();
-  for (int k = tid; k < K; k += nt) {       // one thread per feature column: fixed-order sum over j
-    const double vc = s_vc[k], lvc = log(vc) - log1p(-vc);
-    double acc = 0.0;
-    for (int j = 0; j < J; ++j) {
-      const int q = j * K + k;
-      const double h = sigmoid_d(real[p.roff[B_H] + q]);
-      const double s = sigmoid_d((lvc - (log(h) - log1p(-h))) / p.tau);
-      const double a = G[bl.dZ + q] * s * (1.0 - s) / p.tau;
-      greal[p.roff[B_H] + q] = -a + (1.0 - 2.0 * h);
-      acc += a;
-    }
-    s_gvc[k] = acc / (vc * (1.0 - vc));
-  }
-  __syncthreads();
   if (tid == 0) {   // cumprod backward, v prior Beta(conc, 1), alpha
-    const double ra = real[p.roff[B_ALPHA]], alpha = exp(ra);
+    const double ra = real[p.roff[B_ALPHA]], alpha = aux1[p.roff[B_ALPHA]];
     const double conc = p.use_stick_break ? alpha : alpha / (double)K;
     double suf = 0.0, dconc = 0.0;
     for (int m = K - 1; m >= 0; --m) {
-      const double v = s_v[m];
+      const double v = aux1[p.roff[B_V] + m];
       double gv;
       if (p.use_stick_break) { suf += s_gvc[m] * s_vc[m]; gv = suf / v; } else { gv = s_gvc[m]; }
       greal[p.roff[B_V] + m] = v * (1.0 - v) * (gv + (conc - 1.0) / v) + (1.0 - 2.0 * v);
-      dconc += log(v) + 1.0 / conc;
+      dconc += aux2[p.roff[B_V] + m] + 1.0 / conc;
     }
     const double dalpha = p.use_stick_break ? dconc : dconc / (double)K;
     greal[p.roff[B_ALPHA]] = alpha * dalpha + (p.alpha_a - 1.0) - p.alpha_b * alpha + 1.0;
+    (void)ra;
   }
   __syncthreads();
 
-  // ---- chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
+  // ---- (3) chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
   const long long step = step_dev ? (*step_dev + 1) : p.step_host;
   const double bc1 = 1.0 - pow(p.beta1, (double)step), bc2s = sqrt(1.0 - pow(p.beta2, (double)step));
   auto adam = [&](int t, double g, bool scrub) {
@@ -334,7 +358,6 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
   for (int q = tid; q < R; q += nt) {
     const int b = block_of(p, q);
     const int sz = p.roff[b + 1] - p.roff[b], loc_i = p.toff[b] + (q - p.roff[b]);
-    if (b == B_EPS && !p.model_noisy) continue;
     const double m = theta[loc_i], ls = theta[loc_i + sz], gr = greal[q], e = eps[q];
     double dloc, dsc, dlogsc;
     if (squashed(b)) {
@@ -358,7 +381,6 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
     out_scalars[3] = lq;
     out_scalars[4] = flag ? (double)*flag : 0.0;
   }
-  (void)sh;
 }
 
 __global__ void bump_step_kernel(long long* step_dev) { *step_dev += 1; }
@@ -409,7 +431,7 @@ int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
   out[0] = p.roff[B_COUNT];                 // R: number of global reals (= noise length)
   out[1] = p.n_global;                      // 2R: scrubbed prefix of theta
   out[2] = p.n_global + 2 * p.I * p.J;      // P: length of theta
-  out[3] = 3 * (int64_t)p.roff[B_COUNT];    // stash doubles: real | eps | greal
+  out[3] = 5 * (int64_t)p.roff[B_COUNT];    // stash doubles: real | eps | greal | aux1 | aux2
   return CYTOF_OK;
 }
 
@@ -419,7 +441,7 @@ int launch_global_fwd(const cytof_global_desc* g, const double* theta, const dou
   const int rc = global_make_params(g, &p);
   if (rc != CYTOF_OK) return rc;
   const int R = p.roff[B_COUNT];
-  global_fwd_kernel<<<1, 1024, 0, s>>>(p, theta, eps_in, stash, stash + R, globals,
+  global_fwd_kernel<<<1, 1024, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R, stash + 4 * R, globals,
                                        reinterpret_cast<unsigned long long*>(zmask), scalars);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
@@ -433,9 +455,9 @@ int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, 
   const int rc = global_make_params(g, &p);
   if (rc != CYTOF_OK) return rc;
   const int R = p.roff[B_COUNT];
-  global_bwd_adam_kernel<<<1, 1024, 0, s>>>(p, theta, stash, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
-                                            adam_v, grad_out, out_scalars, reinterpret_cast<long long*>(step_dev),
-                                            flag, do_update);
+  global_bwd_adam_kernel<<<1, 1024, 0, s>>>(p, theta, stash, stash + R, stash + 3 * R, stash + 4 * R, packed,
+                                            scalars_in, stash + 2 * R, adam_m, adam_v, grad_out, out_scalars,
+                                            reinterpret_cast<long long*>(step_dev), flag, do_update);
   if (step_dev && do_update) bump_step_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_dev));
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
