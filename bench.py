@@ -234,9 +234,11 @@ def run_ours(args, w, rank, world, local_rank):
     for t in range(2 + max(3, args.steps // 2)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        if mb is None:
-            eng.y_dev.copy_(y_pin, non_blocking=True)
-            idx = draw_idx(t)
+        if mb is None:      # full batch: sample-by-sample upload overlapped with the per-cell kernel
+            _ = fs.step_from_host(y_pin).tolist()
+            b.record()
+            e_ev.append((a, b))
+            continue
         else:   # minibatch: gather the step's rows on the host, ship rows + indices
             rows = [np.random.choice(n, mb, replace=False) for _ in range(I)]
             sel = torch.cat([torch.from_numpy(r + i * n) for i, r in enumerate(rows)])

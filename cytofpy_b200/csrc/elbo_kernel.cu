@@ -594,7 +594,9 @@ static const Variant* pick_variant(int J, int K, int L0, int L1) {
 
 static size_t fused_smem_bytes(const Variant* v, int J, int K, int L0, int L1) {
   const PartialLayout pl = partial_layout(J, K, L0, L1);
-  return sizeof(float) * (size_t)(kWarps * v->smem_floats_per_warp + v->smem_floats_extra + pl.total);
+  // the J,K<=32 kernel keeps one partial record per warp in shared memory for its final reduction
+  const size_t records = v->smem_floats_extra ? kWarps : 1;
+  return sizeof(float) * (size_t)(kWarps * v->smem_floats_per_warp + v->smem_floats_extra + records * pl.total);
 }
 
 static int g_sm_count[64] = {0};
@@ -614,19 +616,26 @@ constexpr int kMinCellsPerWarp = 4;
 
 int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAMPLES; }
 
-// resident CTAs per SM of one kernel variant (cached; immutable per device + binary)
-static int g_occ[64][16][4] = {};
-static int variant_occupancy(const Variant* v, int noisy, size_t smem) {
+// resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached per
+// device; re-evaluated when a different problem shape changes the shared-memory footprint)
+struct OccEntry { size_t smem, smem_attr; int occ; };
+static OccEntry g_occ[64][16][4] = {};
+static int variant_occupancy(const Variant* v, int fi, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
-  const int vi = (int)(v - kVariants);
-  if (g_occ[dev][vi][noisy] == 0) {
+  OccEntry& e = g_occ[dev][(int)(v - kVariants)][fi];
+  if (e.occ == 0 || e.smem != smem) {
+    if (smem > 48 * 1024 && smem > e.smem_attr) {   // opt in to large dynamic shared memory
+      cudaFuncSetAttribute(v->fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e.smem_attr = smem;
+    }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn[noisy], kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn[fi], kThreads, smem) != cudaSuccess || n < 1) n = 1;
     if (n > kMaxCtasPerSm) n = kMaxCtasPerSm;
-    g_occ[dev][vi][noisy] = n;
+    e.occ = n;
+    e.smem = smem;
   }
-  return g_occ[dev][vi][noisy];
+  return e.occ;
 }
 
 int validate_desc(const cytof_desc* d) {
@@ -721,10 +730,6 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
   if (nblocks > 0) {
     KernelFn fn = v->fn[fi];
-    if (smem > 48 * 1024) {
-      *err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (*err != cudaSuccess) return CYTOF_ECUDA;
-    }
     fn<<<nblocks, kThreads, smem, stream>>>(p);
     *err = cudaGetLastError();
     if (*err != cudaSuccess) return CYTOF_ECUDA;

@@ -144,9 +144,12 @@ elbo_fwdbwd_j32_kernel(const ElboParams p) {
   {
     const unsigned kmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
     const unsigned zrow = ok ? ((unsigned)p.zmask[jj] & kmask) : 0u;
-    unsigned zcol = 0u;
-    if (lane < K)
-      for (int j = 0; j < J; ++j) zcol |= (unsigned)((p.zmask[j] >> lane) & 1ull) << j;
+    unsigned zcol = 0u;     // column `lane` of Z over j = ballot of bit `lane` of every lane's row
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const unsigned bal = __ballot_sync(FULL, (zrow >> k) & 1u);
+      if (lane == k) zcol = bal;
+    }
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       zc[q] = mk2((float)((zcol >> (2 * q)) & 1u), (float)((zcol >> (2 * q + 1)) & 1u));
@@ -447,43 +450,50 @@ elbo_fwdbwd_j32_kernel(const ElboParams p) {
   const float swdd_w = warp_sum(lo2(swdd) + hi2(swdd));
   lqy_l = warp_sum(lqy_l);
   lmiss_l = warp_sum(lmiss_l);
-  double* sdbl = reinterpret_cast<double*>(sred + pl.dbl);
+  // every warp writes its own record into its own shared-memory slice, then all threads add the
+  // kWarps slices element-wise in a fixed order (reproducible, no serial rounds)
+  float* mine = sred + warp * pl.total;
   __syncthreads();
-  for (int w = 0; w < kWarps; ++w) {
-    if (warp == w) {
-      auto put = [&](int off, float v) {
-        if (w == 0) sred[off] = v; else sred[off] += v;
-      };
-      if (ok) {
+  for (int t = lane; t < pl.total; t += 32) mine[t] = 0.f;
+  __syncwarp();
+  if (ok) {
 #pragma unroll
-        for (int l = 0; l < 2 * NP0; ++l) if (l < L0) put(pl.sw0 + l * J + lane, (l & 1) ? hi2(sw0[l / 2]) : lo2(sw0[l / 2]));
+    for (int l = 0; l < 2 * NP0; ++l) if (l < L0) mine[pl.sw0 + l * J + lane] = (l & 1) ? hi2(sw0[l / 2]) : lo2(sw0[l / 2]);
 #pragma unroll
-        for (int l = 0; l < 2 * NP1; ++l) if (l < L1) put(pl.sw1 + l * J + lane, (l & 1) ? hi2(sw1[l / 2]) : lo2(sw1[l / 2]));
+    for (int l = 0; l < 2 * NP1; ++l) if (l < L1) mine[pl.sw1 + l * J + lane] = (l & 1) ? hi2(sw1[l / 2]) : lo2(sw1[l / 2]);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) if (k < K) put(pl.dZ + k * J + lane, (k & 1) ? hi2(dZ[k / 2]) : lo2(dZ[k / 2]));
-        put(pl.dvm + lane, dvm);
-        put(pl.dvls + lane, dvls);
-        put(pl.nm + lane, nm);
-      }
-      if (lane < K) put(pl.gW + lane, gW);
-      if (lane == 0) {
-#pragma unroll
-        for (int l = 0; l < 2 * NP0; ++l) if (l < L0) put(pl.swd0 + l, swd0f[l]);
-#pragma unroll
-        for (int l = 0; l < 2 * NP1; ++l) if (l < L1) put(pl.swd1 + l, swd1f[l]);
-        put(pl.sc + 0, swdd_w);
-        put(pl.sc + 1, sfr);
-        put(pl.sc + 2, sfo);
-        put(pl.sc + 3, 0.f);
-        const double llw = (double)fac * (ll2 * 0.6931471805599453 + (double)lmiss_l);
-        const double lqw = (double)fac * (double)p.scale * (double)lqy_l;
-        if (w == 0) { sdbl[0] = llw; sdbl[1] = lqw; } else { sdbl[0] += llw; sdbl[1] += lqw; }
-      }
-    }
-    __syncthreads();
+    for (int k = 0; k < 32; ++k) if (k < K) mine[pl.dZ + k * J + lane] = (k & 1) ? hi2(dZ[k / 2]) : lo2(dZ[k / 2]);
+    mine[pl.dvm + lane] = dvm;
+    mine[pl.dvls + lane] = dvls;
+    mine[pl.nm + lane] = nm;
   }
+  if (lane < K) mine[pl.gW + lane] = gW;
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < 2 * NP0; ++l) if (l < L0) mine[pl.swd0 + l] = swd0f[l];
+#pragma unroll
+    for (int l = 0; l < 2 * NP1; ++l) if (l < L1) mine[pl.swd1 + l] = swd1f[l];
+    mine[pl.sc + 0] = swdd_w;
+    mine[pl.sc + 1] = sfr;
+    mine[pl.sc + 2] = sfo;
+    double* md = reinterpret_cast<double*>(mine + pl.dbl);
+    md[0] = (double)fac * (ll2 * 0.6931471805599453 + (double)lmiss_l);
+    md[1] = (double)fac * (double)p.scale * (double)lqy_l;
+  }
+  __syncthreads();
   float* out = p.partials + (size_t)blockIdx.x * pl.total;
-  for (int t = threadIdx.x; t < pl.total; t += kThreads) out[t] = sred[t];
+  for (int t = threadIdx.x; t < pl.total; t += kThreads) {
+    if (t >= pl.dbl && t < pl.dbl + 4) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) a += sred[w * pl.total + t];
+    out[t] = a;
+  }
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int w = 0; w < kWarps; ++w) a += reinterpret_cast<const double*>(sred + w * pl.total + pl.dbl)[threadIdx.x];
+    reinterpret_cast<double*>(out + pl.dbl)[threadIdx.x] = a;
+  }
 }
 
 }  // namespace cytof

@@ -87,7 +87,7 @@ class CellEngine:
         """fac_i = N_i / B_i with GLOBAL counts (reference Model.py:257)."""
         cg = counts_global if counts_global is not None else batch.counts
         for i in range(self.I):
-            d.fac[i] = self.N_global[i] / cg[i] if cg[i] > 0 else 0.0
+            d.fac[i] = self.N_global[i] / cg[i] if (cg[i] > 0 and batch.counts[i] > 0) else 0.0
 
     def make_idx(self, idx_list):
         """list of per-sample index collections (numpy / list / range / device tensor) ->

@@ -155,3 +155,50 @@ class FusedStep:
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
         self.launches += 4
         return self.scalars
+
+    def step_from_host(self, y_pinned, update=True):
+        """The same full-batch step with the data matrix in PINNED HOST memory (`y_pinned`:
+        [sum N_i, J] fp32, NaN = missing): sample i is uploaded on a side stream while the per-cell
+        kernel of sample i-1 runs, so the PCIe copy and the compute overlap.  The per-sample packed
+        results are added (one tiny torch op) before the backward of the global part."""
+        m, eng, g = self.model, self.eng, self.g
+        self.t += 1
+        g.step = self.t
+        g.adam_step = self.t
+        g.noise_mode = _lib.NOISE_PHILOX
+        I = eng.I
+        main = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(self.dev)
+            self._parts = torch.zeros((I, self.packed.numel()), dtype=F64, device=self.dev)
+            self._ev = [torch.cuda.Event() for _ in range(I)]
+        cs = self._copy_stream
+        cs.wait_stream(main)                      # the previous step no longer reads y_dev
+        rb = eng.row_base
+        with torch.cuda.stream(cs):
+            for i in range(I):
+                eng.y_dev[rb[i]:rb[i + 1]].copy_(y_pinned[rb[i]:rb[i + 1]], non_blocking=True)
+                self._ev[i].record(cs)
+        stream = C.c_void_p(main.cuda_stream)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.cytof_global_fwd_f64(
+                C.byref(g), _ptr(self.theta), _ptr(None), _ptr(self.stash), _ptr(self.globals),
+                _ptr(self.zmask), _ptr(self.scalars_in), stream))
+        full = Batch(eng.N_local, None, None, step=self.t)
+        cg = m._counts_global(full) or eng.N_local
+        for i in range(I):
+            main.wait_event(self._ev[i])
+            counts = [0] * I
+            counts[i] = eng.N_local[i]
+            eng.fwdbwd_packed(Batch(counts, None, None, step=self.t), self.globals, self.zmask,
+                              self._parts[i], [cg[j] if j == i else 0 for j in range(I)])
+        torch.sum(self._parts, 0, out=self.packed)
+        if m.dist_group is not None:
+            torch.distributed.all_reduce(self.packed, group=m.dist_group)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.cytof_global_bwd_adam_f64(
+                C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
+                _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
+                _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
+        self.launches += 2 + 2 * I
+        return self.scalars
