@@ -57,6 +57,7 @@ _PROTOS = {
     'cytof_global_bwd_adam_f64': (C.c_int, [C.POINTER(GlobalDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                             C.c_int32, _P]),
     'cytof_impute_emit_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P]),
+    'cytof_label_sample_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P]),
     'cytof_noise_emit_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P]),
     'cytof_adam_step_f64': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.c_double, C.c_int64, _P, _P, _P]),

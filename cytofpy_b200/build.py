@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, '_C')
 LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200.so')
-SOURCES = ['elbo_kernel.cu', 'global_part.cu', 'abi.cu']
+SOURCES = ['elbo_kernel.cu', 'global_part.cu', 'labels.cu', 'abi.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -13,6 +13,8 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
                   double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
                   cudaError_t* err);
+int launch_labels(const cytof_desc* d, const float* y, const float* globals, const uint64_t* zmask,
+                  int32_t* lam_out, float* probs_out, cudaStream_t stream, cudaError_t* err);
 struct GlobalParams;
 int global_sizes(const cytof_global_desc* g, int64_t out[4]);
 int launch_global_fwd(const cytof_global_desc* g, const double* theta, const double* eps_in, double* stash,
@@ -193,6 +195,17 @@ int cytof_impute_emit_f32(const cytof_desc* d, const float* y, const int32_t* id
   if (!y || !globals || !y_out) return CYTOF_EINVAL;
   cudaError_t err = cudaSuccess;
   rc = launch_emit(d, y, idx, eps, globals, y_out, nullptr, (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+int cytof_label_sample_f32(const cytof_desc* d, const float* y_imp, const float* globals,
+                           const uint64_t* zmask, int32_t* lam_out, float* probs_out, void* stream) {
+  int rc = validate_desc(d);
+  if (rc != CYTOF_OK) return rc;
+  if (!y_imp || !globals || !zmask || !lam_out) return CYTOF_EINVAL;
+  cudaError_t err = cudaSuccess;
+  rc = launch_labels(d, y_imp, globals, zmask, lam_out, probs_out, (cudaStream_t)stream, &err);
   if (rc == CYTOF_ECUDA) set_cuda_err(err);
   return rc;
 }

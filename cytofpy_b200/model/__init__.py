@@ -12,6 +12,7 @@ from .priors import (compute_Z, default_priors, gen_beta_est, logit, prob_miss, 
 from .variational import ModelParam, VAE  # noqa: E402
 from .core import Model  # noqa: E402
 from .train import check_nan_in_grad, device_minibatch, fit, update  # noqa: E402
+from . import post_proc  # noqa: E402
 
 __all__ = ['compute_Z', 'default_priors', 'gen_beta_est', 'logit', 'prob_miss', 'solve_beta',
-           'ModelParam', 'VAE', 'Model', 'check_nan_in_grad', 'device_minibatch', 'fit', 'update']
+           'ModelParam', 'VAE', 'Model', 'check_nan_in_grad', 'device_minibatch', 'fit', 'update', 'post_proc']

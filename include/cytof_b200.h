@@ -109,6 +109,13 @@ int cytof_impute_emit_f32(const cytof_desc* d, const float* y, const int32_t* id
 /* Writes the standard-normal draws eps_out[C, J] that CYTOF_NOISE_PHILOX uses (test hook). */
 int cytof_noise_emit_f32(const cytof_desc* d, const int32_t* idx, float* eps_out, void* stream);
 
+/* Posterior cluster labels (post_proc/lam_post.py:6-55): for each of the C cells of y_imp[C, J]
+ * (already imputed, no NaN; sample-major as in cell_begin) writes the class probabilities
+ * probs_out[C, K+1] (nullable; class 0 = noisy cell, 1..K = features) and one categorical draw
+ * lam_out[C] keyed by (seed, step, global row).  Forward half of the likelihood, no gradient. */
+int cytof_label_sample_f32(const cytof_desc* d, const float* y_imp, const float* globals,
+                           const uint64_t* zmask, int32_t* lam_out, float* probs_out, void* stream);
+
 /* Adam over a flat fp64 buffer.  n_scrub leading entries get NaN gradients replaced by 0
  * (fit.py:24-30 scrubs the 10 global blocks but not the imputation parameters); *flag (int32,
  * device, may be NULL) is set to 1 if anything was scrubbed.  grad_scale multiplies the raw

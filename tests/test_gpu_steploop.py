@@ -106,3 +106,40 @@ def test_fit_runs_and_improves_elbo(capsys):
     assert e[-20:].mean() > e[:3].mean() + 150
     assert len(out['trace']) >= 30 and 'W' in out['trace'][0]
     assert out['trace'][0]['W'].dist().mean.shape == (3, 9)
+
+
+def test_posterior_label_sampler_matches_oracle():
+    """post_proc.theta + post_proc.sample (reference post_proc/lam_post.py:6-55): class
+    probabilities vs the fp64 oracle, and the categorical draws vs those probabilities."""
+    from oracle import lam_post_port
+    from tests._golden import Case
+    from tests._model_util import build_model
+    c = Case('c_nan_nostick_tau001')
+    dev = torch.device('cuda', 0)
+    mod = build_model(c, dev, noise='philox')
+    pri = cy.model.default_priors(c.y, K=c.K, L=[c.L0, c.L1], y_bounds=[-5., -3.5, -2.])
+    theta, _ = cy.model.post_proc.theta(mod, pri)
+    assert [tuple(t.shape) for t in theta['y']] == [(n, c.J) for n in c.N]
+    assert not any(torch.isnan(t).any().item() for t in theta['y'])          # imputed
+    for t, y0 in zip(theta['y'], c.y):                                        # observed entries untouched
+        obs = ~torch.isnan(y0)
+        assert torch.allclose(t.cpu()[obs], y0[obs].float().double(), atol=1e-6)
+    lam, probs = cy.model.post_proc.sample(theta, mod, return_probs=True, seed=5)
+    th_np = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in theta.items() if k != 'y'}
+    th_np['noisy_sd'] = float(theta['noisy_sd'])
+    th_np['y'] = [t.cpu().numpy() for t in theta['y']]
+    ref = lam_post_port.label_probs(th_np)
+    for i in range(c.I):
+        p = probs[i].cpu().numpy()
+        assert p.shape == (c.N[i], c.K + 1)
+        assert np.max(np.abs(p - ref[i])) < 2e-5
+        assert np.allclose(p.sum(1), 1.0, atol=1e-5)
+        li = lam[i].cpu().numpy()
+        assert li.dtype == np.int64 and li.min() >= 0 and li.max() <= c.K
+        sure = ref[i].max(1) > 0.999
+        assert (li[sure] == ref[i].argmax(1)[sure]).mean() > 0.99
+    # repeated draws follow the probabilities (cell 0 of sample 0)
+    draws = np.stack([cy.model.post_proc.sample(theta, mod, seed=100 + s)[0].cpu().numpy() for s in range(300)])
+    k_star = int(ref[0][:, 1:].mean(0).argmax()) + 1
+    emp = (draws == k_star).mean()
+    assert abs(emp - ref[0][:, k_star].mean()) < 0.03

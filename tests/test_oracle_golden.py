@@ -10,6 +10,7 @@ from oracle import elbo_port as port
 from tests._golden import Case, case_names, rel
 
 F64 = torch.float64
+ROOT_DIR = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))
 
 
 def test_solve_beta_known_answer():
@@ -120,3 +121,43 @@ def _torch_cells(t, rows, eps, fac, cfg, b):
         ll = ll + fac[i] * (L.sum() + torch.nn.functional.logsigmoid(u)[miss].sum())
         lqy = lqy + fac[i] * cfg['scale'] * (-.5 * e * e - t['vls'][i][None] - .5 * LOG2PI)[miss].sum()
     return ll, lqy
+
+
+@pytest.mark.skipif(not __import__('os').path.isdir('/root/reference/cytofpy'),
+                    reason='needs the live reference (build container only)')
+def test_lam_post_port_matches_reference():
+    """oracle/lam_post_port.py vs the live reference post_proc (probabilities recomputed from the
+    reference's own formulas, lam_post.py:20-51, on a sample_params.theta draw)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r)
+torch.distributions.Distribution.set_default_validate_args(False)
+import cytofpy
+from torch.distributions import Normal
+from oracle import lam_post_port
+torch.manual_seed(0); np.random.seed(0)
+y = cytofpy.util.simdata(N=[60, 40], J=6, a_W=[100.]*3, L0=3, L1=2)['data']['y']
+y[0][0, 1] = float('nan')
+pri = cytofpy.model.default_priors(y, K=4, L=[3, 2], y_bounds=[-5., -3.5, -2.])
+mod = cytofpy.model.Model(y=y, priors=pri, verbose=-1)
+th, _ = cytofpy.model.post_proc.sample_params.theta(mod, pri)
+ref = []
+for i in range(mod.I):
+    yi, e, W = th['y'][i], th['eps'][i], th['W'][i]
+    lp0 = e.log() + Normal(0, th['noisy_sd']).log_prob(yi).sum(1, keepdim=True)
+    a0 = Normal(th['mu0'][None, None, :], th['sig'][i]).log_prob(yi[:, :, None]) + th['eta0'][i:i+1].log()
+    a1 = Normal(th['mu1'][None, None, :], th['sig'][i]).log_prob(yi[:, :, None]) + th['eta1'][i:i+1].log()
+    m0, m1 = a0.logsumexp(2), a1.logsumexp(2)
+    f = (th['Z'][None] * m1[:, :, None] + (1 - th['Z'][None]) * m0[:, :, None]).sum(1)
+    lp = torch.cat((lp0, torch.log1p(-e) + W.log()[None] + f), 1)
+    ref.append((lp - lp.logsumexp(1, keepdim=True)).exp().numpy())
+tn = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in th.items() if k != 'y'}
+tn['noisy_sd'] = float(th['noisy_sd']); tn['y'] = [t.numpy() for t in th['y']]
+got = lam_post_port.label_probs(tn)
+print(max(float(np.abs(a - b).max()) for a, b in zip(got, ref)))
+''' % ROOT_DIR
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert float(out.stdout.strip().splitlines()[-1]) < 1e-12
