@@ -7,7 +7,7 @@
 A "step" is one full `update` of the reference (fit.py:32-48): draw the global
 sample, transforms, per-cell ELBO forward+backward over ONE batch (the fused
 CUDA kernel), log prior, entropy, backward to every variational parameter, NaN
-scrub and the Adam step — here 4 kernel launches (cytofpy_b200/model/fused.py).  The default workload is BASELINE.json configs[3]
+scrub and the Adam step — here 8 kernel launches (cytofpy_b200/model/fused.py).  The default workload is BASELINE.json configs[3]
 ("cfg4": full batch, I=8, J=32, K=30, L=5/5) — the configuration the metric
 string names — with 1,000,000 cells PER GPU (weak scaling: rank r holds rows
 [r*125000, (r+1)*125000) of each of the 8 samples; one all-reduce of the
@@ -280,7 +280,9 @@ def run_ours(args, w, rank, world, local_rank):
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_kernel (+finalize)', 'achieved': achieved,
-                         'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         # dram__bytes_read+write of one launch, ncu --set full (profiles/README.md)
+                         'traffic': 131.4e6 if args.workload == 'cfg4' else None,
                          'peak_source': peak_src, 'bytes_per_cell': bytes_cell, 'kernel_ms': k_ms,
                          'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
             'cpu_baseline': cpu,

@@ -32,6 +32,8 @@ struct GlobalParams {
   double tau;
   double delta0_a, delta0_b, delta1_a, delta1_b, sig2_p0, sig2_p1, alpha_a, alpha_b, eps_a, eps_b;
   double eta0_c[CYTOF_MAX_L], eta1_c[CYTOF_MAX_L], W_c[CYTOF_MAX_K];
+  // normalising constants of the priors (pure functions of the hyper-parameters: host lgamma)
+  double n_delta0, n_delta1, n_sig2, n_alpha, n_eps, n_eta0, n_eta1, n_W;
   unsigned long long seed, step;
   // real-vector layout: offset of each block in the R-vector (noise / reals) and in theta
   int roff[B_COUNT + 1];   // roff[b]..roff[b+1]
@@ -87,14 +89,17 @@ __device__ __forceinline__ RowPos row_pos(const GlobalParams& p, int b, int loca
 //   eta0 / eta1 / W element:  aux1 = log z,   aux2 = log(1 - z)   (z = clipped sigmoid)
 //   H element:                aux1 = h                            v element: aux1 = v, aux2 = log v
 //   delta element:            aux1 = exp(real)
-__global__ void __launch_bounds__(1024, 1)
-global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const double* __restrict__ eps_in,
-                  double* __restrict__ real, double* __restrict__ eps_out, double* __restrict__ aux1,
-                  double* __restrict__ aux2, float* __restrict__ globals,
-                  unsigned long long* __restrict__ zmask, double* __restrict__ scalars /* lp, lq_global */) {
+// (1) runs on kElemCtas CTAs (one SM's fp64 rate is the limit of a single CTA: ~10^5 DFMA per
+// step); per-CTA partial sums of lp / lq go to cta_part[2 * blockIdx.x + {0,1}].
+constexpr int kElemCtas = 24;
+constexpr int kElemThreads = 256;
+
+__global__ void __launch_bounds__(kElemThreads)
+global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, const double* __restrict__ eps_in,
+                       double* __restrict__ real, double* __restrict__ eps_out, double* __restrict__ aux1,
+                       double* __restrict__ aux2, float* __restrict__ globals, double* __restrict__ cta_part) {
   __shared__ double sh[32];
-  __shared__ double s_vc[CYTOF_MAX_K];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
@@ -120,20 +125,19 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
       case B_DELTA0: case B_DELTA1: {
         const double d = exp(r), a_ = b == B_DELTA0 ? p.delta0_a : p.delta1_a, b_ = b == B_DELTA0 ? p.delta0_b : p.delta1_b;
         aux1[q] = d;
-        lp += a_ * log(b_) + (a_ - 1.0) * r - b_ * d - lgamma(a_) + r;
+        lp += (b == B_DELTA0 ? p.n_delta0 : p.n_delta1) + (a_ - 1.0) * r - b_ * d + r;
       } break;
       case B_EPS: {
         const double ee = sigmoid_d(r);
         globals[gl.eps + local] = (float)ee;
-        lp += (p.eps_a - 1.0) * log(ee) + (p.eps_b - 1.0) * log1p(-ee) + lgamma(p.eps_a + p.eps_b) - lgamma(p.eps_a) -
-              lgamma(p.eps_b) + log(ee) + log1p(-ee);
+        lp += (p.eps_a - 1.0) * log(ee) + (p.eps_b - 1.0) * log1p(-ee) + p.n_eps + log(ee) + log1p(-ee);
       } break;
       case B_SIG2: {
         globals[gl.sig + local] = (float)exp(0.5 * r);
         if (p.sig2_family == 0)
-          lp += -r - log(p.sig2_p1) - HL2PI - (r - p.sig2_p0) * (r - p.sig2_p0) / (2.0 * p.sig2_p1 * p.sig2_p1) + r;
+          lp += -r + p.n_sig2 - (r - p.sig2_p0) * (r - p.sig2_p0) / (2.0 * p.sig2_p1 * p.sig2_p1) + r;
         else
-          lp += p.sig2_p0 * log(p.sig2_p1) + (p.sig2_p0 - 1.0) * r - p.sig2_p1 * exp(r) - lgamma(p.sig2_p0) + r;
+          lp += p.n_sig2 + (p.sig2_p0 - 1.0) * r - p.sig2_p1 * exp(r) + r;
       } break;
       case B_ETA0: case B_ETA1: case B_W: {
         const RowPos rp = row_pos(p, b, local);
@@ -145,7 +149,7 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
       case B_ALPHA: {
         const double alpha = exp(r);
         aux1[q] = alpha;
-        lp += p.alpha_a * log(p.alpha_b) + (p.alpha_a - 1.0) * r - p.alpha_b * alpha - lgamma(p.alpha_a) + r;
+        lp += p.n_alpha + (p.alpha_a - 1.0) * r - p.alpha_b * alpha + r;
       } break;
       case B_V: {
         const double v = sigmoid_d(r), lv = log(v);
@@ -166,9 +170,23 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
     globals[gl.vm + q] = (float)theta[p.vae_off + (q / J) * 2 * J + (q % J)];
     globals[gl.vls + q] = (float)theta[p.vae_off + (q / J) * 2 * J + J + (q % J)];
   }
-  __syncthreads();   // single CTA: the global writes above are visible block-wide after the barrier
+  lp = block_sum(lp, sh);
+  lq = block_sum(lq, sh);
+  if (threadIdx.x == 0) { cta_part[2 * blockIdx.x] = lp; cta_part[2 * blockIdx.x + 1] = lq; }
+}
 
-  // ---- (2) serial scans (adds / multiplies only)
+// (2) one CTA: serial scans (adds / multiplies only), Z bit mask, final lp / lq
+__global__ void __launch_bounds__(1024, 1)
+global_fwd_scan_kernel(const GlobalParams p, const double* __restrict__ aux1, const double* __restrict__ aux2,
+                       float* __restrict__ globals, unsigned long long* __restrict__ zmask,
+                       const double* __restrict__ cta_part, double* __restrict__ scalars /* lp, lq_global */) {
+  __shared__ double sh[32];
+  __shared__ double s_vc[CYTOF_MAX_K];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
+  double lp = 0.0;
+
   if (tid == 0) {   // mu0 = -cumsum(delta0)   (Model.py:223)
     double c = 0.0;
     for (int l = 0; l < L0; ++l) { c += aux1[p.roff[B_DELTA0] + l]; globals[gl.mu0 + l] = (float)(-c); }
@@ -195,20 +213,19 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
       if (rr0 < 0) continue;
       int n, goff, ro;
       const double* conc;
-      if (rr0 < rows0) { n = L0 - 1; ro = p.roff[B_ETA0] + rr0 * n; conc = p.eta0_c; goff = gl.le0 + rr0 * L0; }
-      else if (rr0 < rows0 + rows1) { const int rr = rr0 - rows0; n = L1 - 1; ro = p.roff[B_ETA1] + rr * n; conc = p.eta1_c; goff = gl.le1 + rr * L1; }
-      else { const int rr = rr0 - rows0 - rows1; n = K - 1; ro = p.roff[B_W] + rr * n; conc = p.W_c; goff = gl.lw + rr * K; }
-      double acc = 0.0, csum = 0.0, lg = 0.0;
+      double norm;
+      if (rr0 < rows0) { n = L0 - 1; ro = p.roff[B_ETA0] + rr0 * n; conc = p.eta0_c; goff = gl.le0 + rr0 * L0; norm = p.n_eta0; }
+      else if (rr0 < rows0 + rows1) { const int rr = rr0 - rows0; n = L1 - 1; ro = p.roff[B_ETA1] + rr * n; conc = p.eta1_c; goff = gl.le1 + rr * L1; norm = p.n_eta1; }
+      else { const int rr = rr0 - rows0 - rows1; n = K - 1; ro = p.roff[B_W] + rr * n; conc = p.W_c; goff = gl.lw + rr * K; norm = p.n_W; }
+      double acc = 0.0;
       for (int k = 0; k < n; ++k) {
         const double ly = aux1[ro + k] + acc;
         globals[goff + k] = (float)ly;
         lp += (conc[k] - 1.0) * ly + aux2[ro + k] + ly;
         acc += aux2[ro + k];
-        csum += conc[k];
-        lg += lgamma(conc[k]);
       }
       globals[goff + n] = (float)acc;
-      lp += (conc[n] - 1.0) * acc + lgamma(csum + conc[n]) - lg - lgamma(conc[n]);
+      lp += (conc[n] - 1.0) * acc + norm;
     }
   }
   __syncthreads();
@@ -219,36 +236,38 @@ global_fwd_kernel(const GlobalParams p, const double* __restrict__ theta, const 
     zmask[j] = m;
   }
   lp = block_sum(lp, sh);
-  lq = block_sum(lq, sh);
-  if (tid == 0) { scalars[0] = lp; scalars[1] = lq; }
+  if (tid == 0) {
+    double lq = 0.0;
+    for (int c = 0; c < kElemCtas; ++c) { lp += cta_part[2 * c]; lq += cta_part[2 * c + 1]; }   // fixed order
+    scalars[0] = lp;
+    scalars[1] = lq;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // packed: [grad block (BlockLayout, doubles) | ll | log_qy] — already summed over ranks.
 // out_scalars: elbo, ll, lp, lq (lq includes log_qy), scrubbed.  grad_out (may be NULL): d loss / d theta.
-__global__ void __launch_bounds__(1024, 1)
-global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const double* __restrict__ real,
-                       const double* __restrict__ eps, const double* __restrict__ aux1, double* __restrict__ aux2,
-                       const double* __restrict__ packed, const double* __restrict__ scalars_in,
-                       double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
-                       double* __restrict__ grad_out, double* __restrict__ out_scalars,
-                       long long* __restrict__ step_dev, int* __restrict__ flag, int do_update) {
-  __shared__ double s_vc[CYTOF_MAX_K], s_lvc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K];
-  const int tid = threadIdx.x, nt = blockDim.x;
+__global__ void __launch_bounds__(kElemThreads)
+global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
+                       double* __restrict__ aux2, const double* __restrict__ packed, double* __restrict__ greal,
+                       int* __restrict__ flag) {
+  __shared__ double s_vc[CYTOF_MAX_K], s_lvc[CYTOF_MAX_K];
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const double* __restrict__ G = packed;
-  if (flag && tid == 0) *flag = 0;
+  if (flag && blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
 
-  // ---- (0) cumprod(v) and logit of it (K values)
-  if (tid == 0) {
+  // ---- (0) cumprod(v) and logit of it (K values; every CTA recomputes its own copy)
+  if (threadIdx.x == 0) {
     double cp = 1.0;
     for (int k = 0; k < K; ++k) { cp = p.use_stick_break ? cp * aux1[p.roff[B_V] + k] : aux1[p.roff[B_V] + k]; s_vc[k] = cp; }
   }
   __syncthreads();
-  for (int k = tid; k < K; k += nt) s_lvc[k] = log(s_vc[k]) - log1p(-s_vc[k]);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_lvc[k] = log(s_vc[k]) - log1p(-s_vc[k]);
   __syncthreads();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  (void)I; (void)J; (void)L0; (void)L1;
 
   // ---- (1) element-parallel part of d(ll + lp)/d real
   for (int q = tid; q < R; q += nt) {
@@ -278,12 +297,27 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
         aux2[q] = a;
         greal[q] = -a + (1.0 - 2.0 * h);
       } break;
-      default: break;                    // delta0 / delta1 / alpha / v: scans below
+      default: break;                    // delta0 / delta1 / alpha / v: scan kernel
     }
+  }
+}
+
+// (2) one CTA: suffix scans (cumsum / cumprod / stick-breaking backward), adds and multiplies only
+__global__ void __launch_bounds__(1024, 1)
+global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
+                       const double* __restrict__ aux2, const double* __restrict__ packed,
+                       double* __restrict__ greal) {
+  __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  const BlockLayout bl = block_layout(I, J, K, L0, L1);
+  const double* __restrict__ G = packed;
+  if (tid == 96) {
+    double cp = 1.0;
+    for (int k = 0; k < K; ++k) { cp = p.use_stick_break ? cp * aux1[p.roff[B_V] + k] : aux1[p.roff[B_V] + k]; s_vc[k] = cp; }
   }
   __syncthreads();
 
-  // ---- (2) serial scans
   if (tid == 0) {
     double suf = 0.0;
     for (int l = L0 - 1; l >= 0; --l) {       // mu0 = -cumsum(delta0)
@@ -339,9 +373,20 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
     greal[p.roff[B_ALPHA]] = alpha * dalpha + (p.alpha_a - 1.0) - p.alpha_b * alpha + 1.0;
     (void)ra;
   }
-  __syncthreads();
+}
 
-  // ---- (3) chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
+// (3) element-parallel: chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
+__global__ void __launch_bounds__(kElemThreads)
+global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const double* __restrict__ eps,
+                   const double* __restrict__ packed, const double* __restrict__ scalars_in,
+                   const double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
+                   double* __restrict__ grad_out, double* __restrict__ out_scalars,
+                   const long long* __restrict__ step_dev, int* __restrict__ flag, int do_update) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  const int R = p.roff[B_COUNT];
+  const BlockLayout bl = block_layout(I, J, K, L0, L1);
+  const double* __restrict__ G = packed;
   const long long step = step_dev ? (*step_dev + 1) : p.step_host;
   const double bc1 = 1.0 - pow(p.beta1, (double)step), bc2s = sqrt(1.0 - pow(p.beta2, (double)step));
   auto adam = [&](int t, double g, bool scrub) {
@@ -372,18 +417,21 @@ global_bwd_adam_kernel(const GlobalParams p, double* __restrict__ theta, const d
     adam(p.vae_off + i * 2 * J + j, G[bl.dvm + q], false);
     adam(p.vae_off + i * 2 * J + J + j, G[bl.dvls + q] - G[bl.dlq + q], false);
   }
-  __syncthreads();
   if (tid == 0) {
     const double ll = G[bl.total], lqy = G[bl.total + 1], lp = scalars_in[0], lq = scalars_in[1] + lqy;
     out_scalars[0] = ll + lp - lq;
     out_scalars[1] = ll;
     out_scalars[2] = lp;
     out_scalars[3] = lq;
-    out_scalars[4] = flag ? (double)*flag : 0.0;
   }
 }
 
-__global__ void bump_step_kernel(long long* step_dev) { *step_dev += 1; }
+// out_scalars[4] = 1 if any NaN gradient was scrubbed in this step (after all CTAs of the Adam kernel)
+__global__ void finish_step_kernel(long long* step_dev, const int* flag, double* out_scalars, int bump) {
+  out_scalars[4] = flag ? (double)*flag : 0.0;
+  if (step_dev && bump) *step_dev += 1;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 static void fill_layout(GlobalParams* p) {
@@ -417,6 +465,21 @@ int global_make_params(const cytof_global_desc* g, GlobalParams* p) {
   p->eps_a = g->eps[0]; p->eps_b = g->eps[1];
   for (int l = 0; l < CYTOF_MAX_L; ++l) { p->eta0_c[l] = g->eta0_conc[l]; p->eta1_c[l] = g->eta1_conc[l]; }
   for (int k = 0; k < CYTOF_MAX_K; ++k) p->W_c[k] = g->W_conc[k];
+  p->n_delta0 = p->delta0_a * log(p->delta0_b) - lgamma(p->delta0_a);
+  p->n_delta1 = p->delta1_a * log(p->delta1_b) - lgamma(p->delta1_a);
+  p->n_alpha = p->alpha_a * log(p->alpha_b) - lgamma(p->alpha_a);
+  p->n_sig2 = p->sig2_family == 0 ? (-log(p->sig2_p1) - 0.9189385332046727)
+                                  : (p->sig2_p0 * log(p->sig2_p1) - lgamma(p->sig2_p0));
+  p->n_eps = lgamma(p->eps_a + p->eps_b) - lgamma(p->eps_a) - lgamma(p->eps_b);
+  {
+    double s0 = 0, l0 = 0, s1 = 0, l1 = 0, sw = 0, lw = 0;
+    for (int l = 0; l < p->L0; ++l) { s0 += p->eta0_c[l]; l0 += lgamma(p->eta0_c[l]); }
+    for (int l = 0; l < p->L1; ++l) { s1 += p->eta1_c[l]; l1 += lgamma(p->eta1_c[l]); }
+    for (int k = 0; k < p->K; ++k) { sw += p->W_c[k]; lw += lgamma(p->W_c[k]); }
+    p->n_eta0 = lgamma(s0) - l0;
+    p->n_eta1 = lgamma(s1) - l1;
+    p->n_W = lgamma(sw) - lw;
+  }
   p->seed = g->seed; p->step = g->step;
   p->grad_scale = g->grad_scale; p->lr = g->lr; p->beta1 = g->beta1; p->beta2 = g->beta2; p->adam_eps = g->adam_eps;
   p->step_host = g->adam_step;
@@ -431,7 +494,7 @@ int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
   out[0] = p.roff[B_COUNT];                 // R: number of global reals (= noise length)
   out[1] = p.n_global;                      // 2R: scrubbed prefix of theta
   out[2] = p.n_global + 2 * p.I * p.J;      // P: length of theta
-  out[3] = 5 * (int64_t)p.roff[B_COUNT];    // stash doubles: real | eps | greal | aux1 | aux2
+  out[3] = 5 * (int64_t)p.roff[B_COUNT] + 2 * kElemCtas;   // stash: real | eps | greal | aux1 | aux2 | CTA partials
   return CYTOF_OK;
 }
 
@@ -441,8 +504,10 @@ int launch_global_fwd(const cytof_global_desc* g, const double* theta, const dou
   const int rc = global_make_params(g, &p);
   if (rc != CYTOF_OK) return rc;
   const int R = p.roff[B_COUNT];
-  global_fwd_kernel<<<1, 1024, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R, stash + 4 * R, globals,
-                                       reinterpret_cast<unsigned long long*>(zmask), scalars);
+  global_fwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
+                                                            stash + 4 * R, globals, stash + 5 * R);
+  global_fwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash + 3 * R, stash + 4 * R, globals,
+                                            reinterpret_cast<unsigned long long*>(zmask), stash + 5 * R, scalars);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
@@ -455,10 +520,13 @@ int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, 
   const int rc = global_make_params(g, &p);
   if (rc != CYTOF_OK) return rc;
   const int R = p.roff[B_COUNT];
-  global_bwd_adam_kernel<<<1, 1024, 0, s>>>(p, theta, stash, stash + R, stash + 3 * R, stash + 4 * R, packed,
-                                            scalars_in, stash + 2 * R, adam_m, adam_v, grad_out, out_scalars,
-                                            reinterpret_cast<long long*>(step_dev), flag, do_update);
-  if (step_dev && do_update) bump_step_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_dev));
+  global_bwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
+                                                            stash + 2 * R, flag);
+  global_bwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed, stash + 2 * R);
+  global_adam_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
+                                                        adam_v, grad_out, out_scalars,
+                                                        reinterpret_cast<const long long*>(step_dev), flag, do_update);
+  finish_step_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_dev), flag, out_scalars, do_update);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }

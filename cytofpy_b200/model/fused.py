@@ -153,7 +153,7 @@ class FusedStep:
                 C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
                 _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
-        self.launches += 4
+        self.launches += 8      # global fwd (2) + per-cell (2) + global bwd / Adam (4)
         return self.scalars
 
     def step_from_host(self, y_pinned, update=True):
@@ -200,5 +200,5 @@ class FusedStep:
                 C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
                 _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
-        self.launches += 2 + 2 * I
+        self.launches += 2 + 2 * I + 4
         return self.scalars
