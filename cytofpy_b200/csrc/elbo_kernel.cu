@@ -19,6 +19,7 @@
 // reproducible results for a given grid.
 #include "common.cuh"
 #include "elbo_kernel_j32.cuh"
+#include "elbo_kernel_mma.cuh"
 
 namespace cytof {
 
@@ -562,6 +563,7 @@ struct Variant {
   int lm0, lm1, jp, kp;
   int smem_floats_per_warp, smem_floats_extra;
   KernelFn fn[4];  // [noisy + 2 * has_idx]
+  bool records_alias;   // the final per-warp records reuse the main-loop shared memory
 };
 #define CYTOF_VARIANT(a, b, jp, kp) \
   { a, b, jp, kp, (jp) * 32 + (kp) * 32, 0, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
@@ -569,12 +571,21 @@ struct Variant {
 #define CYTOF_VARIANT_J32(a, b) \
   { a, b, 1, 1, kCPW * 64, kJ32ConstFloats, { elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
                              elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true> } }
+#define CYTOF_VARIANT_MMA(a, b) \
+  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma_kernel<a, b, false, false>, elbo_fwdbwd_mma_kernel<a, b, true, false>, \
+                             elbo_fwdbwd_mma_kernel<a, b, false, true>, elbo_fwdbwd_mma_kernel<a, b, true, true> }, true }
+#ifndef CYTOF_MMA
+#define CYTOF_MMA 1   // 1: tensor-core kernel (8 cells per warp iteration) for J,K <= 32
+#endif
 #ifndef CYTOF_J32
 #define CYTOF_J32 1   // 1: packed-fp32, two-cells-in-flight kernel for J,K <= 32; 0: first kernel
 #endif
 // ordered by cost: the first variant that fits is used; (8,8) is the padded fallback
 static const Variant kVariants[] = {
-#if CYTOF_J32
+#if CYTOF_MMA
+    CYTOF_VARIANT_MMA(3, 3), CYTOF_VARIANT_MMA(4, 3), CYTOF_VARIANT_MMA(5, 3),
+    CYTOF_VARIANT_MMA(5, 5), CYTOF_VARIANT_MMA(8, 8),
+#elif CYTOF_J32
     CYTOF_VARIANT_J32(3, 3), CYTOF_VARIANT_J32(4, 3), CYTOF_VARIANT_J32(5, 3),
     CYTOF_VARIANT_J32(5, 5), CYTOF_VARIANT_J32(8, 8),
 #else
@@ -596,7 +607,9 @@ static size_t fused_smem_bytes(const Variant* v, int J, int K, int L0, int L1) {
   const PartialLayout pl = partial_layout(J, K, L0, L1);
   // the J,K<=32 kernel keeps one partial record per warp in shared memory for its final reduction
   const size_t records = v->smem_floats_extra ? kWarps : 1;
-  return sizeof(float) * (size_t)(kWarps * v->smem_floats_per_warp + v->smem_floats_extra + records * pl.total);
+  const size_t loop_floats = (size_t)kWarps * v->smem_floats_per_warp + v->smem_floats_extra;
+  if (v->records_alias) return sizeof(float) * (loop_floats > records * pl.total ? loop_floats : records * pl.total);
+  return sizeof(float) * (loop_floats + records * pl.total);
 }
 
 static int g_sm_count[64] = {0};

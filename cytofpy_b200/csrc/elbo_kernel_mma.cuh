@@ -1,0 +1,587 @@
+// Tensor-core variant of the fused ELBO kernel for J <= 32 and K <= 32 (BASELINE cfg1-cfg4).
+//
+// ncu on the packed-fp32 kernel (profiles/README.md, r1c) showed the path is NOT HBM-bound (DRAM
+// 3 %): it is bound by issue slots / the FMA pipe, a third of which went into the three J x K
+// contractions, and by latency (one cell in flight per warp).  BASELINE.json's north star asks
+// for tensor cores in exactly that case.  This kernel
+//   * processes EIGHT cells per warp iteration: the mixture phases keep lane = marker j (so the
+//     (j,l)-indexed statistics stay in the lane's registers) and are unrolled over the 8 cells,
+//     which gives the FMA / MUFU pipes 8 independent instruction streams per warp;
+//   * moves the three contractions of Model.py:246-249 and their backward to warp-level tensor
+//     core MMAs (mma.sync m16n8k8, TF32 operands, FP32 accumulate) with the 8 cells as the N (or
+//     K) dimension:
+//         f^T [k, n] = Z^T[k, j] . D^T[j, n] + log W_k       (A = Z^T constant, B = D tile)
+//         c1^T[j, n] = Z  [j, k] . g^T[k, n]                 (A = Z   constant, B = g tile)
+//         dZ  [j, k] += D^T[j, n] . g [n, k]                 (contraction over the 8 cells)
+//     Z is exactly 0/1 in TF32.  D and g are split x = hi + lo (hi = x rounded to TF32, lo the
+//     exact fp32 remainder), and the products hi.Z + lo.Z (hi.hi + hi.lo + lo.hi for dZ) are
+//     accumulated in fp32, so the result carries ~22 mantissa bits: the 1e-4 / 1e-5 parity bars
+//     hold (single-pass TF32 would not);
+//   * streams y with cp.async (LDGSTS) into a per-warp double buffer one tile ahead.
+// Per-cell scalars (logsumexp over K, noisy class) are evaluated in the accumulator layout of the
+// first MMA (thread (g,t) owns cells 2t, 2t+1 and features g, g+8, g+16, g+24).
+#pragma once
+#include "elbo_kernel_j32.cuh"
+
+namespace cytof {
+
+constexpr int kTile = 8;                 // cells per warp iteration (= N of the MMAs)
+constexpr int kTS = 36;                  // row stride of the per-warp tiles: conflict-free ldmatrix
+constexpr int kTileFloats = kTile * kTS;
+// per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
+constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 16 + 2 * kTile * 32;
+constexpr int kMmaZFloats = 2 * 8 * 32 * 4;   // A-fragment tables of Z^T and Z
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// x = hi + lo with hi = x rounded to TF32 (round half away) and lo the exact remainder, truncated
+// to TF32 (the truncation error is <= 2^-21 |x| and follows the sign of lo, i.e. it is unbiased)
+__device__ __forceinline__ void split_tf32(const float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+// four 8x4 fp32 blocks (ldmatrix on 8x8 b16 tiles): thread (g,t) receives element [g][4m + t] of
+// block m; every lane passes the address of row (lane & 7) of block (lane >> 3)
+__device__ __forceinline__ void ldsm_x4(const float* row_ptr, uint32_t (&r)[4]) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(row_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// running maxima of the two mixtures over packed pair q of the flat component list
+template <int LM0, int NC>
+__device__ __forceinline__ void constexpr_pair_max(const int q, const f2 v, float& M0, float& M1) {
+  const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
+  if (!hi_live) { if (lo1) M1 = fmaxf(M1, lo2(v)); else M0 = fmaxf(M0, lo2(v)); }
+  else if (lo1) M1 = max3(M1, lo2(v), hi2(v));
+  else if (!hi1) M0 = max3(M0, lo2(v), hi2(v));
+  else { M0 = fmaxf(M0, lo2(v)); M1 = fmaxf(M1, hi2(v)); }
+}
+
+template <int LM0, int LM1, bool NOISY, bool HAS_IDX>
+__global__ void __launch_bounds__(kThreads, 1)
+elbo_fwdbwd_mma_kernel(const ElboParams p) {
+  constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;          // components, packed pairs
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;                   // MMA fragment coordinates
+  uint4* sZT = reinterpret_cast<uint4*>(smem);              // [mt][c][lane] A fragments of Z^T (k x j)
+  uint4* sZ = sZT + 8 * 32;                                 // [mt][c][lane] A fragments of Z   (j x k)
+  float* wbase = smem + kMmaZFloats + warp * kMmaWarpFloats;
+  float* sD = wbase;                       // [8][kTS] D_j = A1_j - A0_j
+  float* sA = sD + kTileFloats;            // [8][kTS] A0_j, later c1_j
+  float* sY = sA + kTileFloats;            // [8][kTS] y_j^2 (noisy class)
+  float* sG = sY + kTileFloats;            // [8][kTS] g_k
+  float* sR0 = sG + kTileFloats;           // [8][32] 1/S0
+  float* sR1 = sR0 + kTile * 32;           // [8][32] 1/S1
+  float* sS = sR1 + kTile * 32;            // [16] fac*rho, fac*(1-rho) per cell
+  float* sYb = sS + 16;                    // [2][8][32] y rows, double buffered
+  float* sred = smem;                      // final reduction aliases everything (after the loop)
+
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  int i = 0;
+  while (i + 1 < I && (int)blockIdx.x >= p.blk_begin[i + 1]) ++i;
+  const int nb = p.blk_begin[i + 1] - p.blk_begin[i];
+  const int lb = (int)blockIdx.x - p.blk_begin[i];
+  const long long cb = p.cell_begin[i];
+  const long long Bi = p.cell_begin[i + 1] - cb;
+  const long long c_lo = Bi * lb / nb, c_hi = Bi * (lb + 1) / nb;
+  const long long row_base = p.row_base[i];
+  const unsigned long long grow_base = (unsigned long long)p.row_global[i];
+
+  // ---------------- Z fragment tables (once per CTA) ----------------
+  {
+    const unsigned kmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+    for (int e = threadIdx.x; e < 2 * 8 * 32; e += kThreads) {
+      const int which = e >> 8, mt = (e >> 7) & 1, c = (e >> 5) & 3, ln = e & 31;
+      const int gg = ln >> 2, tt = ln & 3;
+      uint32_t v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = 16 * mt + gg + ((r & 1) ? 8 : 0), col = 8 * c + tt + ((r & 2) ? 4 : 0);
+        const int j = which ? row : col, k = which ? col : row;   // which = 0: Z^T[k][j], 1: Z[j][k]
+        const unsigned zr = j < J ? ((unsigned)p.zmask[j] & kmask) : 0u;
+        v[r] = ((zr >> k) & 1u) ? 0x3f800000u : 0u;
+      }
+      (which ? sZ : sZT)[(mt * 4 + c) * 32 + ln] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+  }
+
+  // ---------------- per-sample constants -> registers ----------------
+  const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
+  const float* __restrict__ G = p.globals;
+  const float sig = G[gl.sig + i];
+  const float inv_sig2 = 1.0f / (sig * sig);
+  const float nh2 = -0.5f * inv_sig2 * kLog2e;
+  const float cbase = (-logf(sig) - kHalfLog2Pi) * kLog2e;
+  const float fac = p.fac[i];
+  const float b0 = G[gl.b + 3 * i], b1 = G[gl.b + 3 * i + 1], b2 = G[gl.b + 3 * i + 2];
+  const bool ok = lane < J;
+  const float okf = ok ? 1.f : 0.f;
+  const int jj = ok ? lane : 0;
+
+  // the LM0 + LM1 mixture components as ONE list (mixture 0 first), processed as packed pairs
+  f2 mu[NPT], cz[NPT];
+  {
+    float m[2 * NPT], c[2 * NPT];
+#pragma unroll
+    for (int x = 0; x < 2 * NPT; ++x) {
+      const bool z1 = x >= LM0;
+      const int l = z1 ? x - LM0 : x, Lz = z1 ? L1 : L0;
+      const bool live = l < Lz && x < LM0 + LM1;
+      const int ll = live ? l : 0;
+      m[x] = live ? G[(z1 ? gl.mu1 : gl.mu0) + ll] : 0.f;
+      c[x] = (ok && live) ? fmaf(G[(z1 ? gl.le1 : gl.le0) + (i * J + jj) * Lz + ll], kLog2e, cbase)
+                          : (l == 0 ? 0.f : kNegBig);
+    }
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) { mu[q] = mk2(m[2 * q], m[2 * q + 1]); cz[q] = mk2(c[2 * q], c[2 * q + 1]); }
+  }
+  const float vm = G[gl.vm + i * J + jj], vls = G[gl.vls + i * J + jj], sd = expf(vls);
+  // log W (log2 domain) of the four feature rows this thread owns in the accumulator layout
+  float lwk[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = g + 8 * r;
+    lwk[r] = k < K ? G[gl.lw + i * K + k] * kLog2e : kNegBig;
+  }
+  float l1me2 = 0.f, zconst2 = 0.f, ninv2s2 = 0.f, inv_s2n = 0.f;
+  if (NOISY) {
+    const float e_i = G[gl.eps + i];
+    l1me2 = log1pf(-e_i) * kLog2e;
+    zconst2 = ((float)J * (-kHalfLog2Pi - logf(p.noisy_sd)) + logf(e_i)) * kLog2e;
+    inv_s2n = 1.0f / (p.noisy_sd * p.noisy_sd);
+    ninv2s2 = -0.5f * inv_s2n * kLog2e;
+  }
+
+  // ---------------- accumulators ----------------
+  f2 sw[NPT], swd[NPT];
+  f2 swdd = bc2(0.f);
+  float dZ[2][4][4];                     // C fragments of dZ (permuted rows / columns, see epilogue)
+  float gW[4] = {0.f, 0.f, 0.f, 0.f};    // sum_n g_k for k = g, g+8, g+16, g+24 (this thread's 2 cells)
+  float dvm = 0.f, dvls = 0.f, nm = 0.f, sfr = 0.f, sfo = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
+  double ll2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) sw[q] = swd[q] = bc2(0.f);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dZ[a][b][c] = 0.f;
+
+  // ---------------- stream the cells of this CTA, 8 per warp iteration ----------------
+  const int32_t* __restrict__ idx = p.idx + (HAS_IDX ? (cb + c_lo) : 0);
+  const float* __restrict__ ybase = p.y + (size_t)row_base * J + lane;
+  const int ncell = (int)(c_hi - c_lo);
+  const int first_row = (int)c_lo;            // full batch: row = c_lo + cell
+  constexpr int STRIDE = kWarps * kTile;
+
+  auto issue_tile = [&](int t0, int buf) {
+    if (ok) {
+#pragma unroll
+      for (int u = 0; u < kTile; ++u) {
+        if (t0 + u < ncell) {
+          const int row = HAS_IDX ? __ldg(idx + t0 + u) : first_row + t0 + u;
+          cp_async4(sYb + (buf * kTile + u) * 32 + lane, ybase + (size_t)row * J);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  int t0 = warp * kTile;
+  int buf = 0;
+  if (t0 < ncell) issue_tile(t0, 0);
+  __syncthreads();   // Z tables visible
+
+  for (; t0 < ncell; t0 += STRIDE, buf ^= 1) {
+    if (t0 + STRIDE < ncell) {
+      issue_tile(t0 + STRIDE, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    const int nvalid = min(kTile, ncell - t0);
+
+    // ================= phase A: lane = marker j, 8 cells =================
+    float ye[kTile];                // observed y, or the N(0,1) draw at missing entries
+    f2 ee[kTile][NPT];
+    unsigned missmask = 0u, anymask = 0u;
+    const f2 nh = bc2(nh2);
+#pragma unroll
+    for (int u = 0; u < kTile; ++u) {
+      const bool valid = u < nvalid;
+      const float yraw = (ok && valid) ? sYb[(buf * kTile + u) * 32 + lane] : 0.f;
+      const bool miss = yraw != yraw;
+      const bool anym = __any_sync(FULL, miss);
+      float yv = yraw;
+      ye[u] = yraw;
+      if (anym) {
+        anymask |= 1u << u;
+        if (miss) {
+          missmask |= 1u << u;
+          const int row = HAS_IDX ? __ldg(idx + t0 + u) : first_row + t0 + u;
+          const float e = p.noise_mode == CYTOF_NOISE_EXTERNAL
+                              ? (p.eps ? __ldg(p.eps + (cb + c_lo + t0 + u) * J + lane) : 0.f)
+                              : philox_normal(p.seed, p.step, grow_base + (unsigned long long)row, lane);
+          ye[u] = e;
+          yv = fmaf(sd, e, vm);
+        }
+      }
+      // ---- mixture log-densities, forward (Model.py:223-233), log2 domain, component pairs
+      const f2 y2 = bc2(yv);
+      f2 v[NPT];
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const f2 d = sub2(y2, mu[q]);
+        v[q] = fma2(mul2(d, nh), d, cz[q]);
+      }
+      float M0 = kNegBig, M1 = kNegBig;
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
+      }
+      const f2 M00 = bc2(M0), M11 = bc2(M1), M01 = mk2(M0, M1);
+      f2 s0 = bc2(0.f), s1 = bc2(0.f);
+      float s0x = 0.f, s1x = 0.f;
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
+        const f2 tt = sub2(v[q], lo1 ? M11 : (hi1 ? M01 : M00));
+        ee[u][q] = mk2(fast_ex2(lo2(tt)), hi_live ? fast_ex2(hi2(tt)) : 0.f);
+        if (lo1) s1 = add2(s1, ee[u][q]);
+        else if (!hi1) s0 = add2(s0, ee[u][q]);
+        else { s0x = lo2(ee[u][q]); s1x = hi2(ee[u][q]); }
+      }
+      const float S0 = (lo2(s0) + hi2(s0)) + s0x, S1 = (lo2(s1) + hi2(s1)) + s1x;
+      const float A0 = M0 + fast_lg2(S0), A1 = M1 + fast_lg2(S1);
+      sR0[u * 32 + lane] = fast_rcp(S0);
+      sR1[u * 32 + lane] = fast_rcp(S1);
+      sD[u * kTS + lane] = okf * (A1 - A0);
+      sA[u * kTS + lane] = okf * A0;
+      if (NOISY) sY[u * kTS + lane] = yv * yv;
+    }
+    __syncwarp();
+
+    // ================= contraction 1: f^T[k, n] = Z^T . D^T + log W (tensor cores) =================
+    uint32_t bh[8], bl[8];      // B fragments of the D tile: block m = markers 4m..4m+3
+    {
+      uint32_t r0[4], r1[4];
+      ldsm_x4(sD + (lane & 7) * kTS + 4 * (lane >> 3), r0);
+      ldsm_x4(sD + (lane & 7) * kTS + 16 + 4 * (lane >> 3), r1);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        split_tf32(__uint_as_float(r0[m]), bh[m], bl[m]);
+        split_tf32(__uint_as_float(r1[m]), bh[4 + m], bl[4 + m]);
+      }
+    }
+    float fT[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      fT[mt][0] = fT[mt][1] = lwk[2 * mt];
+      fT[mt][2] = fT[mt][3] = lwk[2 * mt + 1];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint4 a = sZT[(mt * 4 + c) * 32 + lane];
+        mma_tf32(fT[mt], a, bh[2 * c], bh[2 * c + 1]);
+        mma_tf32(fT[mt], a, bl[2 * c], bl[2 * c + 1]);
+      }
+    }
+    // ---- per-cell scalars in the accumulator layout: this thread owns cells 2*t4, 2*t4+1 and
+    // features g, g+8, g+16, g+24; reductions over k run over the 8 lanes with equal t4
+    const int ca = 2 * t4;
+    float mxa = fmaxf(fmaxf(fT[0][0], fT[0][2]), fmaxf(fT[1][0], fT[1][2]));
+    float mxb = fmaxf(fmaxf(fT[0][1], fT[0][3]), fmaxf(fT[1][1], fT[1][3]));
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      mxa = fmaxf(mxa, __shfl_xor_sync(FULL, mxa, o));
+      mxb = fmaxf(mxb, __shfl_xor_sync(FULL, mxb, o));
+    }
+    float ex[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      ex[mt][0] = fast_ex2(fT[mt][0] - mxa);
+      ex[mt][1] = fast_ex2(fT[mt][1] - mxb);
+      ex[mt][2] = fast_ex2(fT[mt][2] - mxa);
+      ex[mt][3] = fast_ex2(fT[mt][3] - mxb);
+    }
+    f2 rs = mk2((ex[0][0] + ex[0][2]) + (ex[1][0] + ex[1][2]), (ex[0][1] + ex[0][3]) + (ex[1][1] + ex[1][3]));
+    f2 ra, ry = bc2(0.f);
+    {
+      const float4 a4 = *reinterpret_cast<const float4*>(sA + ca * kTS + 4 * g);
+      const float4 b4 = *reinterpret_cast<const float4*>(sA + (ca + 1) * kTS + 4 * g);
+      ra = mk2((a4.x + a4.y) + (a4.z + a4.w), (b4.x + b4.y) + (b4.z + b4.w));
+      if (NOISY) {
+        const float4 c4 = *reinterpret_cast<const float4*>(sY + ca * kTS + 4 * g);
+        const float4 d4 = *reinterpret_cast<const float4*>(sY + (ca + 1) * kTS + 4 * g);
+        ry = mk2((c4.x + c4.y) + (c4.z + c4.w), (d4.x + d4.y) + (d4.z + d4.w));
+      }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      rs = add2(rs, shfl_xor2(rs, o));
+      ra = add2(ra, shfl_xor2(ra, o));
+      if (NOISY) ry = add2(ry, shfl_xor2(ry, o));
+    }
+    float fr2[2], om2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float mx = h ? mxb : mxa;
+      const float ssum = h ? hi2(rs) : lo2(rs);
+      const float a0s = h ? hi2(ra) : lo2(ra);
+      const bool valid = ca + h < nvalid;
+      const float facc = valid ? fac : 0.f;
+      const float lse2 = (mx + a0s) + fast_lg2(ssum);
+      const float rinv = fast_rcp(ssum);
+      float rho = 1.f, omr = 0.f, L2 = lse2;
+      if (NOISY) {
+        const float y2s = h ? hi2(ry) : lo2(ry);
+        const float q2 = lse2 + l1me2;
+        const float z2 = fmaf(ninv2s2, y2s, zconst2);
+        const float dd = q2 - z2;
+        const float tq = fast_ex2(-fabsf(dd));
+        const float r1 = fast_rcp(1.f + tq);
+        L2 = fmaxf(q2, z2) + fast_lg2(1.f + tq);
+        rho = dd >= 0.f ? r1 : tq * r1;
+        omr = dd >= 0.f ? tq * r1 : r1;
+      }
+      if (valid) ll2 += (double)L2;
+      const float fr = facc * rho;
+      fr2[h] = fr;
+      om2[h] = facc * omr;
+      sfr += fr;
+      sfo += om2[h];
+      const float sc = fr * rinv;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        ex[mt][h] *= sc;          // g_k = fac rho softmax_k(f)
+        ex[mt][2 + h] *= sc;
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      gW[2 * mt] += ex[mt][0] + ex[mt][1];
+      gW[2 * mt + 1] += ex[mt][2] + ex[mt][3];
+      sG[ca * kTS + 16 * mt + g] = ex[mt][0];
+      sG[(ca + 1) * kTS + 16 * mt + g] = ex[mt][1];
+      sG[ca * kTS + 16 * mt + g + 8] = ex[mt][2];
+      sG[(ca + 1) * kTS + 16 * mt + g + 8] = ex[mt][3];
+    }
+    if (g == 0) {
+      sS[ca] = fr2[0];
+      sS[ca + 1] = fr2[1];
+      sS[8 + ca] = om2[0];
+      sS[8 + ca + 1] = om2[1];
+    }
+    __syncwarp();
+
+    // ================= contraction 2: c1^T[j, n] = Z . g^T (tensor cores) =================
+    {
+      uint32_t r0[4], r1[4];
+      ldsm_x4(sG + (lane & 7) * kTS + 4 * (lane >> 3), r0);
+      ldsm_x4(sG + (lane & 7) * kTS + 16 + 4 * (lane >> 3), r1);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        split_tf32(__uint_as_float(r0[m]), bh[m], bl[m]);
+        split_tf32(__uint_as_float(r1[m]), bh[4 + m], bl[4 + m]);
+      }
+    }
+    float cT[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) cT[mt][0] = cT[mt][1] = cT[mt][2] = cT[mt][3] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint4 a = sZ[(mt * 4 + c) * 32 + lane];
+        mma_tf32(cT[mt], a, bh[2 * c], bh[2 * c + 1]);
+        mma_tf32(cT[mt], a, bl[2 * c], bl[2 * c + 1]);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {     // c1 overwrites the A0 tile (its sums were taken above)
+      sA[ca * kTS + 16 * mt + g] = cT[mt][0];
+      sA[(ca + 1) * kTS + 16 * mt + g] = cT[mt][1];
+      sA[ca * kTS + 16 * mt + g + 8] = cT[mt][2];
+      sA[(ca + 1) * kTS + 16 * mt + g + 8] = cT[mt][3];
+    }
+
+    // ================= contraction 3: dZ[j, k] += D^T . g over the 8 cells (tensor cores) =================
+    {
+      const float4 d_lo = *reinterpret_cast<const float4*>(sD + t4 * kTS + 4 * g);        // cell t4,   markers 4g..4g+3
+      const float4 d_hi = *reinterpret_cast<const float4*>(sD + (t4 + 4) * kTS + 4 * g);  // cell t4+4
+      const float4 g_lo = *reinterpret_cast<const float4*>(sG + t4 * kTS + 4 * g);        // cell t4,   features 4g..4g+3
+      const float4 g_hi = *reinterpret_cast<const float4*>(sG + (t4 + 4) * kTS + 4 * g);
+      const float dl[4] = {d_lo.x, d_lo.y, d_lo.z, d_lo.w}, dh[4] = {d_hi.x, d_hi.y, d_hi.z, d_hi.w};
+      const float gl4[4] = {g_lo.x, g_lo.y, g_lo.z, g_lo.w}, gh4[4] = {g_hi.x, g_hi.y, g_hi.z, g_hi.w};
+      uint4 ah[2], al[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {   // rows g / g+8 of m-tile mt = markers 4g+2mt / 4g+2mt+1
+        split_tf32(dl[2 * mt], ah[mt].x, al[mt].x);
+        split_tf32(dl[2 * mt + 1], ah[mt].y, al[mt].y);
+        split_tf32(dh[2 * mt], ah[mt].z, al[mt].z);
+        split_tf32(dh[2 * mt + 1], ah[mt].w, al[mt].w);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {   // column g of n-tile nt = feature 4g+nt
+        uint32_t b0h, b0l, b1h, b1l;
+        split_tf32(gl4[nt], b0h, b0l);
+        split_tf32(gh4[nt], b1h, b1l);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_tf32(dZ[mt][nt], ah[mt], b0h, b1h);
+          mma_tf32(dZ[mt][nt], ah[mt], b0l, b1l);
+          mma_tf32(dZ[mt][nt], al[mt], b0h, b1h);
+        }
+      }
+    }
+    __syncwarp();
+
+    // ================= phase B: lane = marker j again, mixture backward =================
+#pragma unroll
+    for (int u = 0; u < kTile; ++u) {
+      const float c1 = okf * sA[u * kTS + lane];
+      const float fr = sS[u];
+      const float c0 = okf * fr - c1;
+      const bool miss = (missmask >> u) & 1u;
+      const float yv = miss ? fmaf(sd, ye[u], vm) : ye[u];
+      const f2 y2 = bc2(yv);
+      const float r0 = c0 * sR0[u * 32 + lane], r1 = c1 * sR1[u * 32 + lane];
+      const f2 R00 = bc2(r0), R11 = bc2(r1), R01 = mk2(r0, r1);
+      f2 wds = bc2(0.f);
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
+        const f2 d = sub2(y2, mu[q]);
+        const f2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[u][q]);
+        const f2 wd = mul2(w, d);
+        acc_add2(sw[q], w);
+        acc_add2(swd[q], wd);
+        acc_fma2(swdd, wd, d);
+        acc_add2(wds, wd);
+      }
+      // logistic missingness (Model.py:269-274) and d/dy chain into the imputation parameters
+      if ((anymask >> u) & 1u) {
+        const float facc = u < nvalid ? fac : 0.f;
+        const float validf = u < nvalid ? 1.f : 0.f;
+        const float wdsum = lo2(wds) + hi2(wds);
+        const float uu = fmaf(fmaf(b2, yv, b1), yv, b0);
+        const float tm = fast_ex2(-fabsf(uu) * kLog2e);
+        const float rr = fast_rcp(1.f + tm);
+        const float ls = -(fmaxf(-uu, 0.f) + kLn2 * fast_lg2(1.f + tm));
+        const float sneg = (uu > 0.f ? tm : 1.f) * rr;   // 1 - sigmoid(u)
+        float dy = -wdsum * inv_sig2 + facc * sneg * fmaf(2.f * b2, yv, b1);
+        if (NOISY) dy = fmaf(-sS[8 + u] * inv_s2n, yv, dy);
+        if (miss) {
+          const float e = ye[u];
+          lmiss_l = fmaf(ls, validf, lmiss_l);
+          dvm += dy;
+          dvls = fmaf(dy * sd, e, dvls);
+          nm += validf;
+          lqy_l = fmaf(fmaf(-0.5f * e, e, -vls - kHalfLog2Pi), validf, lqy_l);
+        }
+      }
+    }
+    __syncwarp();   // the tiles are rewritten by the next iteration
+  }
+
+  // ---------------- CTA reduction (fixed order) and partial record ----------------
+  const PartialLayout pl = partial_layout(J, K, L0, L1);
+  float swdf[2 * NPT];
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) { swdf[2 * q] = warp_sum(lo2(swd[q])); swdf[2 * q + 1] = warp_sum(hi2(swd[q])); }
+  const float swdd_w = warp_sum(lo2(swdd) + hi2(swdd));
+  lqy_l = warp_sum(lqy_l);
+  lmiss_l = warp_sum(lmiss_l);
+  // accumulator-layout sums: features over the 4 lanes of a quad, per-cell scalars over t4 at g == 0
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    gW[r] += __shfl_xor_sync(FULL, gW[r], 1);
+    gW[r] += __shfl_xor_sync(FULL, gW[r], 2);
+  }
+  sfr += __shfl_xor_sync(FULL, sfr, 1);
+  sfr += __shfl_xor_sync(FULL, sfr, 2);
+  sfo += __shfl_xor_sync(FULL, sfo, 1);
+  sfo += __shfl_xor_sync(FULL, sfo, 2);
+  ll2 += __shfl_xor_sync(FULL, ll2, 1);
+  ll2 += __shfl_xor_sync(FULL, ll2, 2);
+
+  float* mine = sred + warp * pl.total;
+  __syncthreads();            // every warp is done with its tiles and with the Z tables
+  for (int t = lane; t < pl.total; t += 32) mine[t] = 0.f;
+  __syncwarp();
+  if (ok) {
+#pragma unroll
+    for (int x = 0; x < NC; ++x) {
+      const float val = (x & 1) ? hi2(sw[x / 2]) : lo2(sw[x / 2]);
+      if (x < LM0) { if (x < L0) mine[pl.sw0 + x * J + lane] = val; }
+      else if (x - LM0 < L1) mine[pl.sw1 + (x - LM0) * J + lane] = val;
+    }
+    mine[pl.dvm + lane] = dvm;
+    mine[pl.dvls + lane] = dvls;
+    mine[pl.nm + lane] = nm;
+  }
+  // dZ fragments: (mt, nt, r) -> marker 4g + 2mt + (r >> 1), feature 8 t4 + 4 (r & 1) + nt
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = 4 * g + 2 * mt + (r >> 1), k = 8 * t4 + 4 * (r & 1) + nt;
+        if (j < J && k < K) mine[pl.dZ + k * J + j] = dZ[mt][nt][r];
+      }
+  if (t4 == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (g + 8 * r < K) mine[pl.gW + g + 8 * r] = gW[r];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int x = 0; x < NC; ++x) {
+      if (x < LM0) { if (x < L0) mine[pl.swd0 + x] = swdf[x]; }
+      else if (x - LM0 < L1) mine[pl.swd1 + (x - LM0)] = swdf[x];
+    }
+    mine[pl.sc + 0] = swdd_w;
+    mine[pl.sc + 1] = sfr;
+    mine[pl.sc + 2] = sfo;
+    double* md = reinterpret_cast<double*>(mine + pl.dbl);
+    md[0] = (double)fac * (ll2 * 0.6931471805599453 + (double)lmiss_l);
+    md[1] = (double)fac * (double)p.scale * (double)lqy_l;
+  }
+  __syncthreads();
+  float* out = p.partials + (size_t)blockIdx.x * pl.total;
+  for (int t = threadIdx.x; t < pl.total; t += kThreads) {
+    if (t >= pl.dbl && t < pl.dbl + 4) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) a += sred[w * pl.total + t];
+    out[t] = a;
+  }
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int w = 0; w < kWarps; ++w) a += reinterpret_cast<const double*>(sred + w * pl.total + pl.dbl)[threadIdx.x];
+    reinterpret_cast<double*>(out + pl.dbl)[threadIdx.x] = a;
+  }
+}
+
+}  // namespace cytof
