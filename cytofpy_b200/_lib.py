@@ -10,13 +10,14 @@ from . import build as _build
 
 MAX_SAMPLES, MAX_J, MAX_K, MAX_L = 32, 64, 64, 8
 NOISE_EXTERNAL, NOISE_PHILOX = 0, 1
+FLAG_NO_MISSING = 1
 
 
 class Desc(C.Structure):
     """mirror of `struct cytof_desc`"""
     _fields_ = [
         ('I', C.c_int32), ('J', C.c_int32), ('K', C.c_int32), ('L0', C.c_int32), ('L1', C.c_int32),
-        ('model_noisy', C.c_int32), ('noise_mode', C.c_int32), ('reserved0', C.c_int32),
+        ('model_noisy', C.c_int32), ('noise_mode', C.c_int32), ('flags', C.c_int32),
         ('noisy_sd', C.c_float), ('scale', C.c_float),
         ('seed', C.c_uint64), ('step', C.c_uint64),
         ('cell_begin', C.c_int64 * (MAX_SAMPLES + 1)),

@@ -562,18 +562,24 @@ using KernelFn = void (*)(const ElboParams);
 struct Variant {
   int lm0, lm1, jp, kp;
   int smem_floats_per_warp, smem_floats_extra;
-  KernelFn fn[4];  // [noisy + 2 * has_idx]
+  KernelFn fn[8];  // [noisy + 2 * has_idx + 4 * no_missing] (the last bit only selects a different kernel in the MMA variants)
   bool records_alias;   // the final per-warp records reuse the main-loop shared memory
 };
 #define CYTOF_VARIANT(a, b, jp, kp) \
   { a, b, jp, kp, (jp) * 32 + (kp) * 32, 0, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
+                                           elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
+                                           elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
                                            elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true> } }
 #define CYTOF_VARIANT_J32(a, b) \
   { a, b, 1, 1, kCPW * 64, kJ32ConstFloats, { elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
+                             elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true>, \
+                             elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
                              elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true> } }
 #define CYTOF_VARIANT_MMA(a, b) \
-  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma_kernel<a, b, false, false>, elbo_fwdbwd_mma_kernel<a, b, true, false>, \
-                             elbo_fwdbwd_mma_kernel<a, b, false, true>, elbo_fwdbwd_mma_kernel<a, b, true, true> }, true }
+  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma_kernel<a, b, false, false, true>, elbo_fwdbwd_mma_kernel<a, b, true, false, true>, \
+                             elbo_fwdbwd_mma_kernel<a, b, false, true, true>, elbo_fwdbwd_mma_kernel<a, b, true, true, true>, \
+                             elbo_fwdbwd_mma_kernel<a, b, false, false, false>, elbo_fwdbwd_mma_kernel<a, b, true, false, false>, \
+                             elbo_fwdbwd_mma_kernel<a, b, false, true, false>, elbo_fwdbwd_mma_kernel<a, b, true, true, false> }, true }
 #ifndef CYTOF_MMA
 #define CYTOF_MMA 1   // 1: tensor-core kernel (8 cells per warp iteration) for J,K <= 32
 #endif
@@ -583,8 +589,7 @@ struct Variant {
 // ordered by cost: the first variant that fits is used; (8,8) is the padded fallback
 static const Variant kVariants[] = {
 #if CYTOF_MMA
-    CYTOF_VARIANT_MMA(3, 3), CYTOF_VARIANT_MMA(4, 3), CYTOF_VARIANT_MMA(5, 3),
-    CYTOF_VARIANT_MMA(5, 5), CYTOF_VARIANT_MMA(8, 8),
+    CYTOF_VARIANT_MMA(3, 3), CYTOF_VARIANT_MMA(5, 3), CYTOF_VARIANT_MMA(5, 5), CYTOF_VARIANT_MMA(8, 8),
 #elif CYTOF_J32
     CYTOF_VARIANT_J32(3, 3), CYTOF_VARIANT_J32(4, 3), CYTOF_VARIANT_J32(5, 3),
     CYTOF_VARIANT_J32(5, 5), CYTOF_VARIANT_J32(8, 8),
@@ -632,7 +637,7 @@ int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAM
 // resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached per
 // device; re-evaluated when a different problem shape changes the shared-memory footprint)
 struct OccEntry { size_t smem, smem_attr; int occ; };
-static OccEntry g_occ[64][16][4] = {};
+static OccEntry g_occ[64][16][8] = {};
 static int variant_occupancy(const Variant* v, int fi, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
@@ -735,7 +740,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15;
   p.partials = reinterpret_cast<float*>(wp);
   const size_t smem = fused_smem_bytes(v, d->J, d->K, d->L0, d->L1);
-  const int fi = (d->model_noisy ? 1 : 0) + (idx ? 2 : 0);
+  const int fi = (d->model_noisy ? 1 : 0) + (idx ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
   const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem));
   const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
   const size_t need = sizeof(float) * (size_t)pl.total * (size_t)nblocks + (wp - reinterpret_cast<uintptr_t>(workspace));

@@ -29,7 +29,7 @@ constexpr int kTile = 8;                 // cells per warp iteration (= N of the
 constexpr int kTS = 36;                  // row stride of the per-warp tiles: conflict-free ldmatrix
 constexpr int kTileFloats = kTile * kTS;
 // per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
-constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 16 + 2 * kTile * 32;
+constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 16 + 2 * kTile * 32 + kTile * 32;
 constexpr int kMmaZFloats = 2 * 8 * 32 * 4;   // A-fragment tables of Z^T and Z
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
@@ -39,9 +39,17 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4 a, const uin
 }
 // x = hi + lo with hi = x rounded to TF32 (round half away) and lo the exact remainder, truncated
 // to TF32 (the truncation error is <= 2^-21 |x| and follows the sign of lo, i.e. it is unbiased)
+#ifndef CYTOF_SPLIT_TRUNC
+#define CYTOF_SPLIT_TRUNC 0   // 1: hi by truncation, lo passed raw (the MMA ignores the low 13 bits)
+#endif
 __device__ __forceinline__ void split_tf32(const float x, uint32_t& hi, uint32_t& lo) {
+#if CYTOF_SPLIT_TRUNC
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+#else
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+#endif
 }
 // four 8x4 fp32 blocks (ldmatrix on 8x8 b16 tiles): thread (g,t) receives element [g][4m + t] of
 // block m; every lane passes the address of row (lane & 7) of block (lane >> 3)
@@ -53,6 +61,10 @@ __device__ __forceinline__ void ldsm_x4(const float* row_ptr, uint32_t (&r)[4]) 
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -73,7 +85,13 @@ __device__ __forceinline__ void constexpr_pair_max(const int q, const f2 v, floa
   else { M0 = fmaxf(M0, lo2(v)); M1 = fmaxf(M1, hi2(v)); }
 }
 
-template <int LM0, int LM1, bool NOISY, bool HAS_IDX>
+#ifndef CYTOF_PIPELINE
+#define CYTOF_PIPELINE 0   // 1: phase B of a tile interleaved with phase A of the warp's next tile
+#endif
+
+// MISSING = false is the caller's promise (cytof_desc.flags & CYTOF_FLAG_NO_MISSING) that y holds
+// no NaN: the imputation pre-pass and the d/dy chain are compiled out.
+template <int LM0, int LM1, bool NOISY, bool HAS_IDX, bool MISSING>
 __global__ void __launch_bounds__(kThreads, 1)
 elbo_fwdbwd_mma_kernel(const ElboParams p) {
   constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;          // components, packed pairs
@@ -92,6 +110,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   float* sR1 = sR0 + kTile * 32;           // [8][32] 1/S1
   float* sS = sR1 + kTile * 32;            // [16] fac*rho, fac*(1-rho) per cell
   float* sYb = sS + 16;                    // [2][8][32] y rows, double buffered
+  float* sW = sYb + 2 * kTile * 32;        // [8][32] sum_l w d (imputation gradient)
   float* sred = smem;                      // final reduction aliases everything (after the loop)
 
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -136,22 +155,37 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   const float okf = ok ? 1.f : 0.f;
   const int jj = ok ? lane : 0;
 
-  // the LM0 + LM1 mixture components as ONE list (mixture 0 first), processed as packed pairs
-  f2 mu[NPT], cz[NPT];
+  // The LM0 + LM1 mixture components as ONE list (mixture 0 first), processed as packed pairs.
+  // With y' = y - m_z (m_z = mid-range of the means of mixture z, keeps |y'| small where the
+  // mixture has mass) the log2-density of component l is
+  //     v_l = cz_l + nh (y' - mu'_l)^2 = nh y'^2 + [ be_l y' + al_l ],   mu'_l = mu_l - m_z,
+  //     be_l = -2 nh mu'_l (lane-uniform),  al_l = cz_l + nh mu'_l^2 (per marker),
+  // and nh y'^2 is common to the components of a mixture: it cancels in the softmax over l and
+  // in D = A1 - A0 up to the two centres, so the forward costs ONE FFMA2 per component pair.
+  f2 mup[NPT], be[NPT], al[NPT];
+  float mc0, mc1;
   {
-    float m[2 * NPT], c[2 * NPT];
+    const float m0a = G[gl.mu0], m0b = G[gl.mu0 + L0 - 1], m1a = G[gl.mu1], m1b = G[gl.mu1 + L1 - 1];
+    mc0 = 0.5f * (m0a + m0b);
+    mc1 = 0.5f * (m1a + m1b);
+    float m[2 * NPT], b[2 * NPT], a[2 * NPT];
 #pragma unroll
     for (int x = 0; x < 2 * NPT; ++x) {
       const bool z1 = x >= LM0;
       const int l = z1 ? x - LM0 : x, Lz = z1 ? L1 : L0;
       const bool live = l < Lz && x < LM0 + LM1;
       const int ll = live ? l : 0;
-      m[x] = live ? G[(z1 ? gl.mu1 : gl.mu0) + ll] : 0.f;
-      c[x] = (ok && live) ? fmaf(G[(z1 ? gl.le1 : gl.le0) + (i * J + jj) * Lz + ll], kLog2e, cbase)
+      m[x] = live ? G[(z1 ? gl.mu1 : gl.mu0) + ll] - (z1 ? mc1 : mc0) : 0.f;
+      b[x] = live ? -2.f * nh2 * m[x] : 0.f;
+      a[x] = (ok && live) ? fmaf(nh2 * m[x], m[x], fmaf(G[(z1 ? gl.le1 : gl.le0) + (i * J + jj) * Lz + ll], kLog2e, cbase))
                           : (l == 0 ? 0.f : kNegBig);
     }
 #pragma unroll
-    for (int q = 0; q < NPT; ++q) { mu[q] = mk2(m[2 * q], m[2 * q + 1]); cz[q] = mk2(c[2 * q], c[2 * q + 1]); }
+    for (int q = 0; q < NPT; ++q) {
+      mup[q] = mk2(m[2 * q], m[2 * q + 1]);
+      be[q] = mk2(b[2 * q], b[2 * q + 1]);
+      al[q] = mk2(a[2 * q], a[2 * q + 1]);
+    }
   }
   const float vm = G[gl.vm + i * J + jj], vls = G[gl.vls + i * J + jj], sd = expf(vls);
   // log W (log2 domain) of the four feature rows this thread owns in the accumulator layout
@@ -171,14 +205,16 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   }
 
   // ---------------- accumulators ----------------
-  f2 sw[NPT], swd[NPT];
-  f2 swdd = bc2(0.f);
+  // sum_n w, sum_n w y' per component (sum w d and sum w d^2 follow in the epilogue) and
+  // sum_n (c0 y0'^2 + c1 y1'^2)
+  f2 sw[NPT], swy[NPT];
+  float sq = 0.f;
   float dZ[2][4][4];                     // C fragments of dZ (permuted rows / columns, see epilogue)
   float gW[4] = {0.f, 0.f, 0.f, 0.f};    // sum_n g_k for k = g, g+8, g+16, g+24 (this thread's 2 cells)
   float dvm = 0.f, dvls = 0.f, nm = 0.f, sfr = 0.f, sfo = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
   double ll2 = 0.0;
 #pragma unroll
-  for (int q = 0; q < NPT; ++q) sw[q] = swd[q] = bc2(0.f);
+  for (int q = 0; q < NPT; ++q) sw[q] = swy[q] = bc2(0.f);
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -188,96 +224,150 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 
   // ---------------- stream the cells of this CTA, 8 per warp iteration ----------------
   const int32_t* __restrict__ idx = p.idx + (HAS_IDX ? (cb + c_lo) : 0);
-  const float* __restrict__ ybase = p.y + (size_t)row_base * J + lane;
+  const float* __restrict__ ysamp = p.y + (size_t)row_base * J;
   const int ncell = (int)(c_hi - c_lo);
   const int first_row = (int)c_lo;            // full batch: row = c_lo + cell
   constexpr int STRIDE = kWarps * kTile;
+  const bool vec16 = J == 32 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;   // 128-byte rows
 
-  auto issue_tile = [&](int t0, int buf) {
-    if (ok) {
+  // y rows of the tile starting at cell tn -> sYb[b]; rows past the end of the range and lanes
+  // >= J are zero-filled, so the arithmetic below needs no validity selects
+  auto issue_tile = [&](const int tn, const int b) {
+    float* dst = sYb + b * (kTile * 32);
+    if (vec16) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h, u = c >> 3, part = c & 7;
+        if (tn + u < ncell) {
+          const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+          cp_async16(dst + u * 32 + 4 * part, ysamp + (size_t)row * 32 + 4 * part);
+        } else {
+          *reinterpret_cast<float4*>(dst + u * 32 + 4 * part) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
 #pragma unroll
       for (int u = 0; u < kTile; ++u) {
-        if (t0 + u < ncell) {
-          const int row = HAS_IDX ? __ldg(idx + t0 + u) : first_row + t0 + u;
-          cp_async4(sYb + (buf * kTile + u) * 32 + lane, ybase + (size_t)row * J);
+        if (ok && tn + u < ncell) {
+          const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+          cp_async4(dst + u * 32 + lane, ysamp + (size_t)row * J + lane);
+        } else {
+          dst[u * 32 + lane] = 0.f;
         }
       }
     }
     cp_async_commit();
   };
 
-  int t0 = warp * kTile;
-  int buf = 0;
-  if (t0 < ncell) issue_tile(t0, 0);
-  __syncthreads();   // Z tables visible
-
-  for (; t0 < ncell; t0 += STRIDE, buf ^= 1) {
-    if (t0 + STRIDE < ncell) {
-      issue_tile(t0 + STRIDE, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    const int nvalid = min(kTile, ncell - t0);
-
-    // ================= phase A: lane = marker j, 8 cells =================
-    float ye[kTile];                // observed y, or the N(0,1) draw at missing entries
-    f2 ee[kTile][NPT];
-    unsigned missmask = 0u, anymask = 0u;
-    const f2 nh = bc2(nh2);
+  // imputation of missing entries (vae.py:17-33): the only branchy part, kept apart so that the
+  // mixture arithmetic is one long basic block.  The N(0,1) draw replaces the NaN in the y buffer.
+  auto prepass = [&](const int tn, const int b, unsigned& mmask, unsigned& amask) {
+    float* src = sYb + b * (kTile * 32);
+    mmask = 0u;
+    amask = 0u;
 #pragma unroll
     for (int u = 0; u < kTile; ++u) {
-      const bool valid = u < nvalid;
-      const float yraw = (ok && valid) ? sYb[(buf * kTile + u) * 32 + lane] : 0.f;
-      const bool miss = yraw != yraw;
-      const bool anym = __any_sync(FULL, miss);
-      float yv = yraw;
-      ye[u] = yraw;
-      if (anym) {
-        anymask |= 1u << u;
-        if (miss) {
-          missmask |= 1u << u;
-          const int row = HAS_IDX ? __ldg(idx + t0 + u) : first_row + t0 + u;
-          const float e = p.noise_mode == CYTOF_NOISE_EXTERNAL
-                              ? (p.eps ? __ldg(p.eps + (cb + c_lo + t0 + u) * J + lane) : 0.f)
-                              : philox_normal(p.seed, p.step, grow_base + (unsigned long long)row, lane);
-          ye[u] = e;
-          yv = fmaf(sd, e, vm);
+      const float yr = src[u * 32 + lane];
+      mmask |= (yr != yr) ? (1u << u) : 0u;
+    }
+    if (__any_sync(FULL, mmask != 0u)) {
+#pragma unroll
+      for (int u = 0; u < kTile; ++u) {
+        const bool miss = (mmask >> u) & 1u;
+        if (__any_sync(FULL, miss)) {
+          amask |= 1u << u;
+          if (miss) {
+            const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+            src[u * 32 + lane] = p.noise_mode == CYTOF_NOISE_EXTERNAL
+                                     ? (p.eps ? __ldg(p.eps + (cb + c_lo + tn + u) * J + lane) : 0.f)
+                                     : philox_normal(p.seed, p.step, grow_base + (unsigned long long)row, lane);
+          }
         }
       }
-      // ---- mixture log-densities, forward (Model.py:223-233), log2 domain, component pairs
-      const f2 y2 = bc2(yv);
-      f2 v[NPT];
-#pragma unroll
-      for (int q = 0; q < NPT; ++q) {
-        const f2 d = sub2(y2, mu[q]);
-        v[q] = fma2(mul2(d, nh), d, cz[q]);
-      }
-      float M0 = kNegBig, M1 = kNegBig;
-#pragma unroll
-      for (int q = 0; q < NPT; ++q) {
-        constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
-      }
-      const f2 M00 = bc2(M0), M11 = bc2(M1), M01 = mk2(M0, M1);
-      f2 s0 = bc2(0.f), s1 = bc2(0.f);
-      float s0x = 0.f, s1x = 0.f;
-#pragma unroll
-      for (int q = 0; q < NPT; ++q) {
-        const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
-        const f2 tt = sub2(v[q], lo1 ? M11 : (hi1 ? M01 : M00));
-        ee[u][q] = mk2(fast_ex2(lo2(tt)), hi_live ? fast_ex2(hi2(tt)) : 0.f);
-        if (lo1) s1 = add2(s1, ee[u][q]);
-        else if (!hi1) s0 = add2(s0, ee[u][q]);
-        else { s0x = lo2(ee[u][q]); s1x = hi2(ee[u][q]); }
-      }
-      const float S0 = (lo2(s0) + hi2(s0)) + s0x, S1 = (lo2(s1) + hi2(s1)) + s1x;
-      const float A0 = M0 + fast_lg2(S0), A1 = M1 + fast_lg2(S1);
-      sR0[u * 32 + lane] = fast_rcp(S0);
-      sR1[u * 32 + lane] = fast_rcp(S1);
-      sD[u * kTS + lane] = okf * (A1 - A0);
-      sA[u * kTS + lane] = okf * A0;
-      if (NOISY) sY[u * kTS + lane] = yv * yv;
     }
+  };
+
+  f2 ee[kTile][NPT];      // exp(a_l - max) of the tile in flight, lane = marker j
+  const f2 nh = bc2(nh2);
+
+  // mixture log-densities of cell u, forward (Model.py:223-233), log2 domain, component pairs
+  auto phase_a = [&](const int u, const float* src, const unsigned mmask) {
+    const float x = src[u * 32 + lane];
+    const float yv = (MISSING && ((mmask >> u) & 1u)) ? fmaf(sd, x, vm) : x;
+    const float y0 = yv - mc0, y1 = yv - mc1;
+    const f2 Y00 = bc2(y0), Y11 = bc2(y1), Y01 = mk2(y0, y1);
+    f2 v[NPT];
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
+      v[q] = fma2(be[q], lo1 ? Y11 : (hi1 ? Y01 : Y00), al[q]);
+    }
+    float M0 = kNegBig, M1 = kNegBig;
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
+    const f2 M00 = bc2(M0), M11 = bc2(M1), M01 = mk2(M0, M1);
+    f2 s0 = bc2(0.f), s1 = bc2(0.f);
+    float s0x = 0.f, s1x = 0.f;
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
+      const f2 tt = sub2(v[q], lo1 ? M11 : (hi1 ? M01 : M00));
+      ee[u][q] = mk2(fast_ex2(lo2(tt)), hi_live ? fast_ex2(hi2(tt)) : 0.f);
+      if (lo1) s1 = add2(s1, ee[u][q]);
+      else if (!hi1) s0 = add2(s0, ee[u][q]);
+      else { s0x = lo2(ee[u][q]); s1x = hi2(ee[u][q]); }
+    }
+    const float S0 = (lo2(s0) + hi2(s0)) + s0x, S1 = (lo2(s1) + hi2(s1)) + s1x;
+    const float A0 = fmaf(nh2 * y0, y0, M0) + fast_lg2(S0), A1 = fmaf(nh2 * y1, y1, M1) + fast_lg2(S1);
+    sR0[u * 32 + lane] = fast_rcp(S0);
+    sR1[u * 32 + lane] = fast_rcp(S1);
+    sD[u * kTS + lane] = okf * (A1 - A0);
+    sA[u * kTS + lane] = okf * A0;
+    if (NOISY) sY[u * kTS + lane] = yv * yv;
+  };
+
+  // mixtures of cell u, backward: w_zl = c_z p_zl; statistics sum w and sum w y' per component,
+  // sum c_z y_z'^2 per cell (sum_l w_zl = c_z) -- three FMA-pipe ops per component pair
+  auto phase_b = [&](const int u, const float* src, const unsigned mmask, const unsigned amask) {
+    const float c1 = okf * sA[u * kTS + lane];
+    const float c0 = okf * sS[u] - c1;
+    const float x = src[u * 32 + lane];
+    const float yv = (MISSING && ((mmask >> u) & 1u)) ? fmaf(sd, x, vm) : x;
+    const float y0 = yv - mc0, y1 = yv - mc1;
+    const f2 Y00 = bc2(y0), Y11 = bc2(y1), Y01 = mk2(y0, y1);
+    const float r0 = c0 * sR0[u * 32 + lane], r1 = c1 * sR1[u * 32 + lane];
+    const f2 R00 = bc2(r0), R11 = bc2(r1), R01 = mk2(r0, r1);
+    sq = fmaf(c0 * y0, y0, fmaf(c1 * y1, y1, sq));
+    f2 wm = bc2(0.f);
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
+      const f2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[u][q]);
+      acc_add2(sw[q], w);
+      acc_fma2(swy[q], w, lo1 ? Y11 : (hi1 ? Y01 : Y00));
+      if (MISSING) acc_fma2(wm, w, mup[q]);
+    }
+    // sum_l w_l d_l = c0 y0' + c1 y1' - sum_l w_l mu'_l: only the imputation gradient needs it
+    if (MISSING && amask) sW[u * 32 + lane] = fmaf(c0, y0, c1 * y1) - (lo2(wm) + hi2(wm));
+  };
+
+  int t0 = warp * kTile;
+  int cur = 0;
+  unsigned missmask = 0u, anymask = 0u;
+  if (t0 < ncell) {       // prologue: phase A of this warp's first tile
+    issue_tile(t0, 0);
+    cp_async_wait<0>();
+    __syncwarp();
+    if (MISSING) prepass(t0, 0, missmask, anymask);
+#pragma unroll
+    for (int u = 0; u < kTile; ++u) phase_a(u, sYb, missmask);
+    if (t0 + STRIDE < ncell) issue_tile(t0 + STRIDE, 1);
+  }
+  __syncthreads();   // Z tables visible
+
+  for (; t0 < ncell; t0 += STRIDE, cur ^= 1) {
+    const int nvalid = min(kTile, ncell - t0);
+    const bool has_next = t0 + STRIDE < ncell;
     __syncwarp();
 
     // ================= contraction 1: f^T[k, n] = Z^T . D^T + log W (tensor cores) =================
@@ -457,60 +547,78 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     }
     __syncwarp();
 
-    // ================= phase B: lane = marker j again, mixture backward =================
+    // ===== phase B of this tile, software-pipelined with phase A of the warp's NEXT tile: the
+    // backward is FMA-pipe work, the forward is MUFU work, and cell u of the next tile reuses the
+    // registers cell u of this tile has just released -- one basic block, both pipes busy
+    const float* ycur = sYb + cur * (kTile * 32);
+    unsigned miss_n = 0u, any_n = 0u;
+    if (has_next) {
+      const float* ynxt = sYb + (cur ^ 1) * (kTile * 32);
+      cp_async_wait<0>();
+      __syncwarp();
+      if (MISSING) prepass(t0 + STRIDE, cur ^ 1, miss_n, any_n);
+#if CYTOF_PIPELINE
 #pragma unroll
-    for (int u = 0; u < kTile; ++u) {
-      const float c1 = okf * sA[u * kTS + lane];
-      const float fr = sS[u];
-      const float c0 = okf * fr - c1;
-      const bool miss = (missmask >> u) & 1u;
-      const float yv = miss ? fmaf(sd, ye[u], vm) : ye[u];
-      const f2 y2 = bc2(yv);
-      const float r0 = c0 * sR0[u * 32 + lane], r1 = c1 * sR1[u * 32 + lane];
-      const f2 R00 = bc2(r0), R11 = bc2(r1), R01 = mk2(r0, r1);
-      f2 wds = bc2(0.f);
-#pragma unroll
-      for (int q = 0; q < NPT; ++q) {
-        const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
-        const f2 d = sub2(y2, mu[q]);
-        const f2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[u][q]);
-        const f2 wd = mul2(w, d);
-        acc_add2(sw[q], w);
-        acc_add2(swd[q], wd);
-        acc_fma2(swdd, wd, d);
-        acc_add2(wds, wd);
+      for (int u = 0; u < kTile; ++u) {
+        phase_b(u, ycur, missmask, anymask);
+        phase_a(u, ynxt, miss_n);
       }
-      // logistic missingness (Model.py:269-274) and d/dy chain into the imputation parameters
-      if ((anymask >> u) & 1u) {
+#else
+#pragma unroll
+      for (int u = 0; u < kTile; ++u) phase_b(u, ycur, missmask, anymask);
+#pragma unroll
+      for (int u = 0; u < kTile; ++u) phase_a(u, ynxt, miss_n);
+#endif
+    } else {
+#pragma unroll
+      for (int u = 0; u < kTile; ++u) phase_b(u, ycur, missmask, anymask);
+    }
+    // logistic missingness (Model.py:269-274) and d/dy chain into the imputation parameters
+    if (MISSING && anymask) {
+#pragma unroll
+      for (int u = 0; u < kTile; ++u) {     // branch-free: lanes without a missing entry add 0
+        const bool miss = (missmask >> u) & 1u;
+        const float mf = (miss && u < nvalid) ? 1.f : 0.f;
+        const float x = ycur[u * 32 + lane];
+        const float e = miss ? x : 0.f;
+        const float yv = miss ? fmaf(sd, e, vm) : x;
         const float facc = u < nvalid ? fac : 0.f;
-        const float validf = u < nvalid ? 1.f : 0.f;
-        const float wdsum = lo2(wds) + hi2(wds);
         const float uu = fmaf(fmaf(b2, yv, b1), yv, b0);
         const float tm = fast_ex2(-fabsf(uu) * kLog2e);
         const float rr = fast_rcp(1.f + tm);
         const float ls = -(fmaxf(-uu, 0.f) + kLn2 * fast_lg2(1.f + tm));
         const float sneg = (uu > 0.f ? tm : 1.f) * rr;   // 1 - sigmoid(u)
-        float dy = -wdsum * inv_sig2 + facc * sneg * fmaf(2.f * b2, yv, b1);
+        float dy = -sW[u * 32 + lane] * inv_sig2 + facc * sneg * fmaf(2.f * b2, yv, b1);
         if (NOISY) dy = fmaf(-sS[8 + u] * inv_s2n, yv, dy);
-        if (miss) {
-          const float e = ye[u];
-          lmiss_l = fmaf(ls, validf, lmiss_l);
-          dvm += dy;
-          dvls = fmaf(dy * sd, e, dvls);
-          nm += validf;
-          lqy_l = fmaf(fmaf(-0.5f * e, e, -vls - kHalfLog2Pi), validf, lqy_l);
-        }
+        dy = miss ? dy : 0.f;
+        lmiss_l = fmaf(ls, mf, lmiss_l);
+        dvm += dy;
+        dvls = fmaf(dy * sd, e, dvls);
+        nm += mf;
+        lqy_l = fmaf(fmaf(-0.5f * e, e, -vls - kHalfLog2Pi), mf, lqy_l);
       }
     }
-    __syncwarp();   // the tiles are rewritten by the next iteration
+    __syncwarp();   // every lane is done with this tile's y buffer and scalars
+    if (t0 + 2 * STRIDE < ncell) issue_tile(t0 + 2 * STRIDE, cur);
+    missmask = miss_n;
+    anymask = any_n;
   }
 
   // ---------------- CTA reduction (fixed order) and partial record ----------------
   const PartialLayout pl = partial_layout(J, K, L0, L1);
+  // sum w d = sum w y' - mu' sum w;  sum w d^2 = sum c y'^2 - sum_l mu'_l (2 sum w y' - mu'_l sum w)
   float swdf[2 * NPT];
+  float swdd_l = sq;
 #pragma unroll
-  for (int q = 0; q < NPT; ++q) { swdf[2 * q] = warp_sum(lo2(swd[q])); swdf[2 * q + 1] = warp_sum(hi2(swd[q])); }
-  const float swdd_w = warp_sum(lo2(swdd) + hi2(swdd));
+  for (int x = 0; x < 2 * NPT; ++x) {
+    const float m = (x & 1) ? hi2(mup[x / 2]) : lo2(mup[x / 2]);
+    const float a = (x & 1) ? hi2(sw[x / 2]) : lo2(sw[x / 2]);
+    const float b = (x & 1) ? hi2(swy[x / 2]) : lo2(swy[x / 2]);
+    const float dsum = fmaf(-m, a, b);
+    swdd_l -= m * (b + dsum);
+    swdf[x] = warp_sum(dsum);
+  }
+  const float swdd_w = warp_sum(swdd_l);
   lqy_l = warp_sum(lqy_l);
   lmiss_l = warp_sum(lmiss_l);
   // accumulator-layout sums: features over the 4 lanes of a quad, per-cell scalars over t4 at g == 0

@@ -53,6 +53,9 @@ class CellEngine:
         self.seed = int(seed)
         # device-resident data: [sum N_i, J] fp32, NaN = missing
         self.y_dev = torch.cat([t.to(torch.float32) for t in y], 0).contiguous().to(self.device)
+        # the reference derives m = isnan(y) once (fit.py:66); an all-false mask lets the library
+        # use the kernels without the imputation path (cytof_desc.flags)
+        self.no_missing = not any(bool(torch.isnan(t).any()) for t in y)
         self.b_dev = torch.as_tensor(b, dtype=F64).reshape(self.I, 3).to(self.device)
         d = self._desc(Batch(self.N_local))
         self.g_off = _lib.layout(d, 'globals')
@@ -73,6 +76,7 @@ class CellEngine:
             noise_mode = _lib.NOISE_EXTERNAL if batch.eps is not None else _lib.NOISE_PHILOX
         d.noise_mode = noise_mode
         d.noisy_sd, d.scale = self.noisy_sd, self.scale
+        d.flags = _lib.FLAG_NO_MISSING if self.no_missing else 0
         d.seed, d.step = self.seed & (2 ** 64 - 1), batch.step
         cb = 0
         for i in range(self.I):

@@ -156,12 +156,15 @@ class FusedStep:
         self.launches += 8      # global fwd (2) + per-cell (2) + global bwd / Adam (4)
         return self.scalars
 
-    def step_from_host(self, y_pinned, update=True):
+    def step_from_host(self, y_pinned, update=True, no_missing=False):
         """The same full-batch step with the data matrix in PINNED HOST memory (`y_pinned`:
         [sum N_i, J] fp32, NaN = missing): sample i is uploaded on a side stream while the per-cell
         kernel of sample i-1 runs, so the PCIe copy and the compute overlap.  The per-sample packed
-        results are added (one tiny torch op) before the backward of the global part."""
+        results are added (one tiny torch op) before the backward of the global part.
+        `no_missing=True` is the caller's statement that `y_pinned` holds no NaN (checked once on
+        the host by whoever owns the matrix); otherwise the imputation path stays compiled in."""
         m, eng, g = self.model, self.eng, self.g
+        eng.no_missing = bool(no_missing)
         self.t += 1
         g.step = self.t
         g.adam_step = self.t

@@ -50,6 +50,11 @@ extern "C" {
 #define CYTOF_NOISE_EXTERNAL 0 /* eps[C,J] supplied (parity mode; only missing entries are read) */
 #define CYTOF_NOISE_PHILOX 1   /* in-kernel Philox4x32-10 keyed by (seed, step, global row, marker) */
 
+/* cytof_desc.flags: the caller's promise that y contains no NaN (the reference computes
+ * m = isnan(y) once in fit.py:66; a data set whose mask is all-false may say so).  Lets the
+ * library pick kernels without the imputation path; a NaN in y then yields a NaN ELBO. */
+#define CYTOF_FLAG_NO_MISSING 1
+
 /* One ELBO evaluation ("step") over C = sum_i B_i cells.
  * The step's cell list is sample-major: cells [cell_begin[i], cell_begin[i+1]) belong to sample i.
  * Cell c of sample i reads row  row_base[i] + (idx ? idx[c] : c - cell_begin[i])  of y. */
@@ -57,7 +62,7 @@ typedef struct cytof_desc {
   int32_t I, J, K, L0, L1;
   int32_t model_noisy; /* Model.py:259-266 on/off */
   int32_t noise_mode;  /* CYTOF_NOISE_* */
-  int32_t reserved0;
+  int32_t flags;       /* CYTOF_FLAG_* (0 = none) */
   float noisy_sd; /* sqrt(priors['noisy_var']), Model.py:148 */
   float scale;    /* vae.py:41 */
   uint64_t seed;  /* Philox key   */

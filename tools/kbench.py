@@ -47,6 +47,7 @@ def main():
     # build the engine around the already-resident matrix (avoid a host round trip)
     CellEngine.__init__(eng, [torch.zeros((1, J))] * I, dev, K, L0, L1, True, 10 ** .5, 1.0, parts[7])
     eng.y_dev = y
+    eng.no_missing = a.nan == 0
     eng.N_local = eng.N_global = [n] * I
     eng.row_base = np.arange(I + 1, dtype=np.int64) * n
     if a.mb:
