@@ -280,10 +280,10 @@ def run_ours(args, w, rank, world, local_rank):
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
-            'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_kernel (+finalize)', 'achieved': achieved,
+            'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_mma_kernel (+finalize)', 'achieved': achieved,
                          'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read+write of one launch, ncu --set full (profiles/README.md)
-                         'traffic': 131.4e6 if args.workload == 'cfg4' else None,
+                         'traffic': 136.0e6 if args.workload == 'cfg4' else None,
                          'peak_source': peak_src, 'bytes_per_cell': bytes_cell, 'kernel_ms': k_ms,
                          'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
             'cpu_baseline': cpu,

@@ -439,48 +439,52 @@ elbo_fwdbwd_kernel(const ElboParams p) {
   for (int t = threadIdx.x; t < pl.total; t += kThreads) out[t] = sred[t];
 }
 
-// One thread per output of the gradient block (+ ll, log_qy): sums the per-CTA records of
-// the relevant sample(s) in fp64, fixed order, and applies the per-sample scalings.
+// kFinLanes threads per output of the gradient block (+ ll, log_qy): lane s sums the per-CTA
+// records s, s + kFinLanes, ... of the relevant sample(s) in fp64, the lanes are combined by a
+// fixed butterfly (=> reproducible for a given grid), then the per-sample scalings are applied.
+constexpr int kFinLanes = 8;
 __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
                                      double* __restrict__ ll_lqy, double* __restrict__ packed) {
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const PartialLayout pl = partial_layout(J, K, L0, L1);
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= bl.total + 2) return;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = gt / kFinLanes, sub = gt % kFinLanes;
+  if (t >= bl.total + 2) return;      // whole lane groups leave together
+  const unsigned gmask = ((1u << kFinLanes) - 1u) << ((threadIdx.x & 31) / kFinLanes * kFinLanes);
   const float* __restrict__ P = p.partials;
   const float* __restrict__ G = p.globals;
-  auto sum_range = [&](int b0, int b1, int off) -> double {
-    // 8 independent loads in flight per thread; the summation ORDER stays fixed (reproducible)
-    double a = 0.0;
-    int b = b0;
-    for (; b + 8 <= b1; b += 8) {
-      float v[8];
+  auto group_sum = [&](double a) -> double {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(P + (size_t)(b + u) * pl.total + off);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a += (double)v[u];
-    }
-    for (; b < b1; ++b) a += (double)__ldg(P + (size_t)b * pl.total + off);
+    for (int o = 1; o < kFinLanes; o <<= 1) a += __shfl_xor_sync(gmask, a, o);
     return a;
+  };
+  auto sum_range = [&](int b0, int b1, int off) -> double {
+    // 4 independent loads in flight per lane, 8 lanes per output
+    double a = 0.0;
+    int b = b0 + sub;
+    for (; b + 3 * kFinLanes < b1; b += 4 * kFinLanes) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(P + (size_t)(b + u * kFinLanes) * pl.total + off);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a += (double)v[u];
+    }
+    for (; b < b1; b += kFinLanes) a += (double)__ldg(P + (size_t)b * pl.total + off);
+    return group_sum(a);
   };
   auto sum_sample = [&](int i, int off) -> double { return sum_range(p.blk_begin[i], p.blk_begin[i + 1], off); };
   if (t >= bl.total) {  // ll, log_qy
     const int which = t - bl.total;
     double a = 0.0;
-    int b = 0;
-    for (; b + 8 <= p.nblocks; b += 8) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = reinterpret_cast<const double*>(P + (size_t)(b + u) * pl.total + pl.dbl)[which];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a += v[u];
-    }
-    for (; b < p.nblocks; ++b)
+    for (int b = sub; b < p.nblocks; b += kFinLanes)
       a += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
-    if (ll_lqy) ll_lqy[which] = a;
-    if (packed) packed[t] = a;
+    a = group_sum(a);
+    if (sub == 0) {
+      if (ll_lqy) ll_lqy[which] = a;
+      if (packed) packed[t] = a;
+    }
     return;
   }
   double r = 0.0;
@@ -526,8 +530,10 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     const int q = t - bl.dlq, i = q / J, j = q % J;
     r = -(double)p.fac[i] * (double)p.scale * sum_sample(i, pl.nm + j);
   }
-  if (grad_block) grad_block[t] = (float)r;
-  if (packed) packed[t] = r;
+  if (sub == 0) {
+    if (grad_block) grad_block[t] = (float)r;
+    if (packed) packed[t] = r;
+  }
 }
 
 // y_out[C,J] = imputed minibatch (vae.py:33); eps_out[C,J] = the Philox draws.
@@ -753,7 +759,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     if (*err != cudaSuccess) return CYTOF_ECUDA;
   }
   const int nout = bl.total + 2;
-  elbo_finalize_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(p, grad_block, ll_lqy, packed);
+  elbo_finalize_kernel<<<(nout * kFinLanes + 127) / 128, 128, 0, stream>>>(p, grad_block, ll_lqy, packed);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }

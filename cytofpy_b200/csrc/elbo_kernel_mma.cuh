@@ -86,7 +86,7 @@ __device__ __forceinline__ void constexpr_pair_max(const int q, const f2 v, floa
 }
 
 #ifndef CYTOF_PIPELINE
-#define CYTOF_PIPELINE 0   // 1: phase B of a tile interleaved with phase A of the warp's next tile
+#define CYTOF_PIPELINE 1   // 1: phase B of a tile interleaved with phase A of the warp's next tile
 #endif
 
 // MISSING = false is the caller's promise (cytof_desc.flags & CYTOF_FLAG_NO_MISSING) that y holds
