@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "elbo_kernel_j32.cuh"
 #include "elbo_kernel_mma.cuh"
+#include "elbo_kernel_mma4.cuh"
 
 namespace cytof {
 
@@ -570,7 +571,9 @@ struct Variant {
   int smem_floats_per_warp, smem_floats_extra;
   KernelFn fn[8];  // [noisy + 2 * has_idx + 4 * no_missing] (the last bit only selects a different kernel in the MMA variants)
   bool records_alias;   // the final per-warp records reuse the main-loop shared memory
+  int threads;          // CTA size (0 = kThreads)
 };
+static int variant_threads(const Variant* v) { return v->threads ? v->threads : kThreads; }
 #define CYTOF_VARIANT(a, b, jp, kp) \
   { a, b, jp, kp, (jp) * 32 + (kp) * 32, 0, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
                                            elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
@@ -586,15 +589,23 @@ struct Variant {
                              elbo_fwdbwd_mma_kernel<a, b, false, true, true>, elbo_fwdbwd_mma_kernel<a, b, true, true, true>, \
                              elbo_fwdbwd_mma_kernel<a, b, false, false, false>, elbo_fwdbwd_mma_kernel<a, b, true, false, false>, \
                              elbo_fwdbwd_mma_kernel<a, b, false, true, false>, elbo_fwdbwd_mma_kernel<a, b, true, true, false> }, true }
+#define CYTOF_VARIANT_MMA4(a, b) \
+  { a, b, 1, 1, kQWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma4_kernel<a, b, false, false, true>, elbo_fwdbwd_mma4_kernel<a, b, true, false, true>, \
+                             elbo_fwdbwd_mma4_kernel<a, b, false, true, true>, elbo_fwdbwd_mma4_kernel<a, b, true, true, true>, \
+                             elbo_fwdbwd_mma4_kernel<a, b, false, false, false>, elbo_fwdbwd_mma4_kernel<a, b, true, false, false>, \
+                             elbo_fwdbwd_mma4_kernel<a, b, false, true, false>, elbo_fwdbwd_mma4_kernel<a, b, true, true, false> }, true, kQThreads }
 #ifndef CYTOF_MMA
-#define CYTOF_MMA 1   // 1: tensor-core kernel (8 cells per warp iteration) for J,K <= 32
+#define CYTOF_MMA 1   // 1: tensor-core kernel, 8 cells per warp iteration, 8 warps/SM (fastest measured);
+                      // 2: 4 cells per iteration, 12 warps/SM (elbo_kernel_mma4.cuh: issue 56 % but +28 % instructions)
 #endif
 #ifndef CYTOF_J32
 #define CYTOF_J32 1   // 1: packed-fp32, two-cells-in-flight kernel for J,K <= 32; 0: first kernel
 #endif
 // ordered by cost: the first variant that fits is used; (8,8) is the padded fallback
 static const Variant kVariants[] = {
-#if CYTOF_MMA
+#if CYTOF_MMA == 2
+    CYTOF_VARIANT_MMA4(3, 3), CYTOF_VARIANT_MMA4(5, 3), CYTOF_VARIANT_MMA4(5, 5), CYTOF_VARIANT_MMA4(8, 8),
+#elif CYTOF_MMA
     CYTOF_VARIANT_MMA(3, 3), CYTOF_VARIANT_MMA(5, 3), CYTOF_VARIANT_MMA(5, 5), CYTOF_VARIANT_MMA(8, 8),
 #elif CYTOF_J32
     CYTOF_VARIANT_J32(3, 3), CYTOF_VARIANT_J32(4, 3), CYTOF_VARIANT_J32(5, 3),
@@ -617,8 +628,9 @@ static const Variant* pick_variant(int J, int K, int L0, int L1) {
 static size_t fused_smem_bytes(const Variant* v, int J, int K, int L0, int L1) {
   const PartialLayout pl = partial_layout(J, K, L0, L1);
   // the J,K<=32 kernel keeps one partial record per warp in shared memory for its final reduction
-  const size_t records = v->smem_floats_extra ? kWarps : 1;
-  const size_t loop_floats = (size_t)kWarps * v->smem_floats_per_warp + v->smem_floats_extra;
+  const size_t nwarps = variant_threads(v) / 32;
+  const size_t records = v->smem_floats_extra ? nwarps : 1;
+  const size_t loop_floats = nwarps * v->smem_floats_per_warp + v->smem_floats_extra;
   if (v->records_alias) return sizeof(float) * (loop_floats > records * pl.total ? loop_floats : records * pl.total);
   return sizeof(float) * (loop_floats + records * pl.total);
 }
@@ -654,7 +666,7 @@ static int variant_occupancy(const Variant* v, int fi, size_t smem) {
       e.smem_attr = smem;
     }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn[fi], kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn[fi], variant_threads(v), smem) != cudaSuccess || n < 1) n = 1;
     if (n > kMaxCtasPerSm) n = kMaxCtasPerSm;
     e.occ = n;
     e.smem = smem;
@@ -754,7 +766,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
   if (nblocks > 0) {
     KernelFn fn = v->fn[fi];
-    fn<<<nblocks, kThreads, smem, stream>>>(p);
+    fn<<<nblocks, variant_threads(v), smem, stream>>>(p);
     *err = cudaGetLastError();
     if (*err != cudaSuccess) return CYTOF_ECUDA;
   }

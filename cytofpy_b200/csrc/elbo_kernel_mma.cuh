@@ -21,6 +21,7 @@
 // Per-cell scalars (logsumexp over K, noisy class) are evaluated in the accumulator layout of the
 // first MMA (thread (g,t) owns cells 2t, 2t+1 and features g, g+8, g+16, g+24).
 #pragma once
+#include <cstdio>
 #include "elbo_kernel_j32.cuh"
 
 namespace cytof {
@@ -31,6 +32,24 @@ constexpr int kTileFloats = kTile * kTS;
 // per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
 constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 16 + 2 * kTile * 32 + kTile * 32;
 constexpr int kMmaZFloats = 2 * 8 * 32 * 4;   // A-fragment tables of Z^T and Z
+
+
+// Packed fp32 through the CUDA 12.9 sm_100 intrinsics (FFMA2 / FADD2 / FMUL2 on float2): unlike
+// the inline-PTX pairs of elbo_kernel_j32.cuh the compiler sees the two halves, so no MOVs are
+// spent on packing and unpacking register pairs.
+__device__ __forceinline__ float2 mkp(float lo, float hi) { return make_float2(lo, hi); }
+__device__ __forceinline__ float2 bcp(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float lo2(float2 a) { return a.x; }
+__device__ __forceinline__ float hi2(float2 a) { return a.y; }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ void acc_add2(float2& acc, float2 x) { acc = __fadd2_rn(acc, x); }
+__device__ __forceinline__ void acc_fma2(float2& acc, float2 a, float2 b) { acc = __ffma2_rn(a, b, acc); }
+__device__ __forceinline__ float2 shfl_xor2(float2 a, int o) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, a.x, o), __shfl_xor_sync(0xffffffffu, a.y, o));
+}
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -77,7 +96,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 
 // running maxima of the two mixtures over packed pair q of the flat component list
 template <int LM0, int NC>
-__device__ __forceinline__ void constexpr_pair_max(const int q, const f2 v, float& M0, float& M1) {
+__device__ __forceinline__ void constexpr_pair_max(const int q, const float2 v, float& M0, float& M1) {
   const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
   if (!hi_live) { if (lo1) M1 = fmaxf(M1, lo2(v)); else M0 = fmaxf(M0, lo2(v)); }
   else if (lo1) M1 = max3(M1, lo2(v), hi2(v));
@@ -162,7 +181,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   //     be_l = -2 nh mu'_l (lane-uniform),  al_l = cz_l + nh mu'_l^2 (per marker),
   // and nh y'^2 is common to the components of a mixture: it cancels in the softmax over l and
   // in D = A1 - A0 up to the two centres, so the forward costs ONE FFMA2 per component pair.
-  f2 mup[NPT], be[NPT], al[NPT];
+  float2 mup[NPT], be[NPT], al[NPT];
   float mc0, mc1;
   {
     const float m0a = G[gl.mu0], m0b = G[gl.mu0 + L0 - 1], m1a = G[gl.mu1], m1b = G[gl.mu1 + L1 - 1];
@@ -182,9 +201,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     }
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
-      mup[q] = mk2(m[2 * q], m[2 * q + 1]);
-      be[q] = mk2(b[2 * q], b[2 * q + 1]);
-      al[q] = mk2(a[2 * q], a[2 * q + 1]);
+      mup[q] = mkp(m[2 * q], m[2 * q + 1]);
+      be[q] = mkp(b[2 * q], b[2 * q + 1]);
+      al[q] = mkp(a[2 * q], a[2 * q + 1]);
     }
   }
   const float vm = G[gl.vm + i * J + jj], vls = G[gl.vls + i * J + jj], sd = expf(vls);
@@ -207,14 +226,14 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   // ---------------- accumulators ----------------
   // sum_n w, sum_n w y' per component (sum w d and sum w d^2 follow in the epilogue) and
   // sum_n (c0 y0'^2 + c1 y1'^2)
-  f2 sw[NPT], swy[NPT];
+  float2 sw[NPT], swy[NPT];
   float sq = 0.f;
   float dZ[2][4][4];                     // C fragments of dZ (permuted rows / columns, see epilogue)
   float gW[4] = {0.f, 0.f, 0.f, 0.f};    // sum_n g_k for k = g, g+8, g+16, g+24 (this thread's 2 cells)
   float dvm = 0.f, dvls = 0.f, nm = 0.f, sfr = 0.f, sfo = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
   double ll2 = 0.0;
 #pragma unroll
-  for (int q = 0; q < NPT; ++q) sw[q] = swy[q] = bc2(0.f);
+  for (int q = 0; q < NPT; ++q) sw[q] = swy[q] = bcp(0.f);
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -287,16 +306,20 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     }
   };
 
-  f2 ee[kTile][NPT];      // exp(a_l - max) of the tile in flight, lane = marker j
-  const f2 nh = bc2(nh2);
+  float2 ee[kTile][NPT];      // exp(a_l - max) of the tile in flight, lane = marker j
+  const float2 nh = bcp(nh2);
 
-  // mixture log-densities of cell u, forward (Model.py:223-233), log2 domain, component pairs
-  auto phase_a = [&](const int u, const float* src, const unsigned mmask) {
+  // mixture log-densities of cell u, forward (Model.py:223-233), log2 domain, component pairs.
+  // Two halves: a1 issues the 10 ex2 of the cell; a2 (called one cell later in the loops below, so
+  // that the MUFU pipe already works on the next cell's exponentials while the sums of this one
+  // settle) takes the logs / reciprocal and writes the tiles.
+  struct AState { float S0, S1, B0, B1, yy; };
+  auto phase_a1 = [&](const int u, const float* src, const unsigned mmask) -> AState {
     const float x = src[u * 32 + lane];
     const float yv = (MISSING && ((mmask >> u) & 1u)) ? fmaf(sd, x, vm) : x;
     const float y0 = yv - mc0, y1 = yv - mc1;
-    const f2 Y00 = bc2(y0), Y11 = bc2(y1), Y01 = mk2(y0, y1);
-    f2 v[NPT];
+    const float2 Y00 = bcp(y0), Y11 = bcp(y1), Y01 = mkp(y0, y1);
+    float2 v[NPT];
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
       const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
@@ -305,25 +328,34 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     float M0 = kNegBig, M1 = kNegBig;
 #pragma unroll
     for (int q = 0; q < NPT; ++q) constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
-    const f2 M00 = bc2(M0), M11 = bc2(M1), M01 = mk2(M0, M1);
-    f2 s0 = bc2(0.f), s1 = bc2(0.f);
+    const float2 M00 = bcp(M0), M11 = bcp(M1), M01 = mkp(M0, M1);
+    float2 s0 = bcp(0.f), s1 = bcp(0.f);
     float s0x = 0.f, s1x = 0.f;
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
       const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
-      const f2 tt = sub2(v[q], lo1 ? M11 : (hi1 ? M01 : M00));
-      ee[u][q] = mk2(fast_ex2(lo2(tt)), hi_live ? fast_ex2(hi2(tt)) : 0.f);
+      const float2 tt = sub2(v[q], lo1 ? M11 : (hi1 ? M01 : M00));
+      ee[u][q] = mkp(fast_ex2(lo2(tt)), hi_live ? fast_ex2(hi2(tt)) : 0.f);
       if (lo1) s1 = add2(s1, ee[u][q]);
       else if (!hi1) s0 = add2(s0, ee[u][q]);
       else { s0x = lo2(ee[u][q]); s1x = hi2(ee[u][q]); }
     }
-    const float S0 = (lo2(s0) + hi2(s0)) + s0x, S1 = (lo2(s1) + hi2(s1)) + s1x;
-    const float A0 = fmaf(nh2 * y0, y0, M0) + fast_lg2(S0), A1 = fmaf(nh2 * y1, y1, M1) + fast_lg2(S1);
-    sR0[u * 32 + lane] = fast_rcp(S0);
-    sR1[u * 32 + lane] = fast_rcp(S1);
+    AState st;
+    st.S0 = (lo2(s0) + hi2(s0)) + s0x;
+    st.S1 = (lo2(s1) + hi2(s1)) + s1x;
+    st.B0 = fmaf(nh2 * y0, y0, M0);      // A_z = B_z + lg2(S_z)
+    st.B1 = fmaf(nh2 * y1, y1, M1);
+    st.yy = yv * yv;
+    return st;
+  };
+  auto phase_a2 = [&](const int u, const AState& st) {
+    const float A0 = st.B0 + fast_lg2(st.S0), A1 = st.B1 + fast_lg2(st.S1);
+    const float rr = fast_rcp(st.S0 * st.S1);      // one reciprocal for both mixtures (S in [1, L])
+    sR0[u * 32 + lane] = rr * st.S1;
+    sR1[u * 32 + lane] = rr * st.S0;
     sD[u * kTS + lane] = okf * (A1 - A0);
     sA[u * kTS + lane] = okf * A0;
-    if (NOISY) sY[u * kTS + lane] = yv * yv;
+    if (NOISY) sY[u * kTS + lane] = st.yy;
   };
 
   // mixtures of cell u, backward: w_zl = c_z p_zl; statistics sum w and sum w y' per component,
@@ -334,15 +366,15 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     const float x = src[u * 32 + lane];
     const float yv = (MISSING && ((mmask >> u) & 1u)) ? fmaf(sd, x, vm) : x;
     const float y0 = yv - mc0, y1 = yv - mc1;
-    const f2 Y00 = bc2(y0), Y11 = bc2(y1), Y01 = mk2(y0, y1);
+    const float2 Y00 = bcp(y0), Y11 = bcp(y1), Y01 = mkp(y0, y1);
     const float r0 = c0 * sR0[u * 32 + lane], r1 = c1 * sR1[u * 32 + lane];
-    const f2 R00 = bc2(r0), R11 = bc2(r1), R01 = mk2(r0, r1);
+    const float2 R00 = bcp(r0), R11 = bcp(r1), R01 = mkp(r0, r1);
     sq = fmaf(c0 * y0, y0, fmaf(c1 * y1, y1, sq));
-    f2 wm = bc2(0.f);
+    float2 wm = bcp(0.f);
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
       const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
-      const f2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[u][q]);
+      const float2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[u][q]);
       acc_add2(sw[q], w);
       acc_fma2(swy[q], w, lo1 ? Y11 : (hi1 ? Y01 : Y00));
       if (MISSING) acc_fma2(wm, w, mup[q]);
@@ -351,6 +383,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     if (MISSING && amask) sW[u * 32 + lane] = fmaf(c0, y0, c1 * y1) - (lo2(wm) + hi2(wm));
   };
 
+#ifdef CYTOF_PHASE_CLOCKS
+  long long clkS = 0, clkBA = 0;
+  int ntiles = 0;
+#endif
   int t0 = warp * kTile;
   int cur = 0;
   unsigned missmask = 0u, anymask = 0u;
@@ -359,8 +395,16 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     cp_async_wait<0>();
     __syncwarp();
     if (MISSING) prepass(t0, 0, missmask, anymask);
+    {
+      AState prev = phase_a1(0, sYb, missmask);
 #pragma unroll
-    for (int u = 0; u < kTile; ++u) phase_a(u, sYb, missmask);
+      for (int u = 1; u < kTile; ++u) {
+        const AState now = phase_a1(u, sYb, missmask);
+        phase_a2(u - 1, prev);
+        prev = now;
+      }
+      phase_a2(kTile - 1, prev);
+    }
     if (t0 + STRIDE < ncell) issue_tile(t0 + STRIDE, 1);
   }
   __syncthreads();   // Z tables visible
@@ -369,6 +413,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     const int nvalid = min(kTile, ncell - t0);
     const bool has_next = t0 + STRIDE < ncell;
     __syncwarp();
+#ifdef CYTOF_PHASE_CLOCKS
+    const long long ck0 = clock64();
+#endif
 
     // ================= contraction 1: f^T[k, n] = Z^T . D^T + log W (tensor cores) =================
     uint32_t bh[8], bl[8];      // B fragments of the D tile: block m = markers 4m..4m+3
@@ -415,16 +462,16 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       ex[mt][2] = fast_ex2(fT[mt][2] - mxa);
       ex[mt][3] = fast_ex2(fT[mt][3] - mxb);
     }
-    f2 rs = mk2((ex[0][0] + ex[0][2]) + (ex[1][0] + ex[1][2]), (ex[0][1] + ex[0][3]) + (ex[1][1] + ex[1][3]));
-    f2 ra, ry = bc2(0.f);
+    float2 rs = mkp((ex[0][0] + ex[0][2]) + (ex[1][0] + ex[1][2]), (ex[0][1] + ex[0][3]) + (ex[1][1] + ex[1][3]));
+    float2 ra, ry = bcp(0.f);
     {
       const float4 a4 = *reinterpret_cast<const float4*>(sA + ca * kTS + 4 * g);
       const float4 b4 = *reinterpret_cast<const float4*>(sA + (ca + 1) * kTS + 4 * g);
-      ra = mk2((a4.x + a4.y) + (a4.z + a4.w), (b4.x + b4.y) + (b4.z + b4.w));
+      ra = mkp((a4.x + a4.y) + (a4.z + a4.w), (b4.x + b4.y) + (b4.z + b4.w));
       if (NOISY) {
         const float4 c4 = *reinterpret_cast<const float4*>(sY + ca * kTS + 4 * g);
         const float4 d4 = *reinterpret_cast<const float4*>(sY + (ca + 1) * kTS + 4 * g);
-        ry = mk2((c4.x + c4.y) + (c4.z + c4.w), (d4.x + d4.y) + (d4.z + d4.w));
+        ry = mkp((c4.x + c4.y) + (c4.z + c4.w), (d4.x + d4.y) + (d4.z + d4.w));
       }
     }
 #pragma unroll
@@ -547,6 +594,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     }
     __syncwarp();
 
+#ifdef CYTOF_PHASE_CLOCKS
+    const long long ck1 = clock64();
+    clkS += ck1 - ck0;
+#endif
     // ===== phase B of this tile, software-pipelined with phase A of the warp's NEXT tile: the
     // backward is FMA-pipe work, the forward is MUFU work, and cell u of the next tile reuses the
     // registers cell u of this tile has just released -- one basic block, both pipes busy
@@ -558,16 +609,27 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       __syncwarp();
       if (MISSING) prepass(t0 + STRIDE, cur ^ 1, miss_n, any_n);
 #if CYTOF_PIPELINE
+      phase_b(0, ycur, missmask, anymask);
+      AState prev = phase_a1(0, ynxt, miss_n);
 #pragma unroll
-      for (int u = 0; u < kTile; ++u) {
+      for (int u = 1; u < kTile; ++u) {
         phase_b(u, ycur, missmask, anymask);
-        phase_a(u, ynxt, miss_n);
+        const AState now = phase_a1(u, ynxt, miss_n);
+        phase_a2(u - 1, prev);
+        prev = now;
       }
+      phase_a2(kTile - 1, prev);
 #else
 #pragma unroll
       for (int u = 0; u < kTile; ++u) phase_b(u, ycur, missmask, anymask);
+      AState prev = phase_a1(0, ynxt, miss_n);
 #pragma unroll
-      for (int u = 0; u < kTile; ++u) phase_a(u, ynxt, miss_n);
+      for (int u = 1; u < kTile; ++u) {
+        const AState now = phase_a1(u, ynxt, miss_n);
+        phase_a2(u - 1, prev);
+        prev = now;
+      }
+      phase_a2(kTile - 1, prev);
 #endif
     } else {
 #pragma unroll
@@ -602,7 +664,15 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     if (t0 + 2 * STRIDE < ncell) issue_tile(t0 + 2 * STRIDE, cur);
     missmask = miss_n;
     anymask = any_n;
+#ifdef CYTOF_PHASE_CLOCKS
+    clkBA += clock64() - ck1;
+    ++ntiles;
+#endif
   }
+#ifdef CYTOF_PHASE_CLOCKS
+  if (blockIdx.x == 3 && lane == 0)
+    printf("warp %d tiles %d  stage S %lld cyc/tile  B+A %lld cyc/tile\n", warp, ntiles, clkS / max(ntiles, 1), clkBA / max(ntiles, 1));
+#endif
 
   // ---------------- CTA reduction (fixed order) and partial record ----------------
   const PartialLayout pl = partial_layout(J, K, L0, L1);
