@@ -30,7 +30,7 @@ constexpr int kTile = 8;                 // cells per warp iteration (= N of the
 constexpr int kTS = 36;                  // row stride of the per-warp tiles: conflict-free ldmatrix
 constexpr int kTileFloats = kTile * kTS;
 // per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
-constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 16 + 2 * kTile * 32 + kTile * 32;
+constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 32 + 2 * kTile * 32 + kTile * 32;
 constexpr int kMmaZFloats = 2 * 8 * 32 * 4;   // A-fragment tables of Z^T and Z
 
 
@@ -127,8 +127,8 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   float* sG = sY + kTileFloats;            // [8][kTS] g_k
   float* sR0 = sG + kTileFloats;           // [8][32] 1/S0
   float* sR1 = sR0 + kTile * 32;           // [8][32] 1/S1
-  float* sS = sR1 + kTile * 32;            // [16] fac*rho, fac*(1-rho) per cell
-  float* sYb = sS + 16;                    // [2][8][32] y rows, double buffered
+  float* sS = sR1 + kTile * 32;            // [0..7] fac*rho, [8..15] fac*(1-rho), [16..23] fac*rho/sum_k e_k per cell
+  float* sYb = sS + 32;                    // [2][8][32] y rows, double buffered
   float* sW = sYb + 2 * kTile * 32;        // [8][32] sum_l w d (imputation gradient)
   float* sred = smem;                      // final reduction aliases everything (after the loop)
 
@@ -429,6 +429,27 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
         split_tf32(__uint_as_float(r1[m]), bh[4 + m], bl[4 + m]);
       }
     }
+    // this thread owns cells 2*t4, 2*t4+1 and features g, g+8, g+16, g+24 in the accumulator
+    // layout; reductions over k (and over the markers below) run over the 8 lanes with equal t4
+    const int ca = 2 * t4;
+    // sum_j A0_j and sum_j y_j^2 of the two cells: independent of the MMAs, issued first so that
+    // their shuffle rounds overlap the accumulator chains
+    float2 ra, ry = bcp(0.f);
+    {
+      const float4 a4 = *reinterpret_cast<const float4*>(sA + ca * kTS + 4 * g);
+      const float4 b4 = *reinterpret_cast<const float4*>(sA + (ca + 1) * kTS + 4 * g);
+      ra = mkp((a4.x + a4.y) + (a4.z + a4.w), (b4.x + b4.y) + (b4.z + b4.w));
+      if (NOISY) {
+        const float4 c4 = *reinterpret_cast<const float4*>(sY + ca * kTS + 4 * g);
+        const float4 d4 = *reinterpret_cast<const float4*>(sY + (ca + 1) * kTS + 4 * g);
+        ry = mkp((c4.x + c4.y) + (c4.z + c4.w), (d4.x + d4.y) + (d4.z + d4.w));
+      }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      ra = add2(ra, shfl_xor2(ra, o));
+      if (NOISY) ry = add2(ry, shfl_xor2(ry, o));
+    }
     float fT[2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -444,9 +465,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
         mma_tf32(fT[mt], a, bl[2 * c], bl[2 * c + 1]);
       }
     }
-    // ---- per-cell scalars in the accumulator layout: this thread owns cells 2*t4, 2*t4+1 and
-    // features g, g+8, g+16, g+24; reductions over k run over the 8 lanes with equal t4
-    const int ca = 2 * t4;
     float mxa = fmaxf(fmaxf(fT[0][0], fT[0][2]), fmaxf(fT[1][0], fT[1][2]));
     float mxb = fmaxf(fmaxf(fT[0][1], fT[0][3]), fmaxf(fT[1][1], fT[1][3]));
 #pragma unroll
@@ -454,6 +472,8 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       mxa = fmaxf(mxa, __shfl_xor_sync(FULL, mxa, o));
       mxb = fmaxf(mxb, __shfl_xor_sync(FULL, mxb, o));
     }
+    // un-normalised softmax numerators e_k = 2^(f_k - max): the second contraction runs on them
+    // (c1 = fac rho / sum_k e_k * Z e), so it does not wait for the logsumexp / noisy-class chain
     float ex[2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -461,26 +481,41 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       ex[mt][1] = fast_ex2(fT[mt][1] - mxb);
       ex[mt][2] = fast_ex2(fT[mt][2] - mxa);
       ex[mt][3] = fast_ex2(fT[mt][3] - mxb);
+      sG[ca * kTS + 16 * mt + g] = ex[mt][0];
+      sG[(ca + 1) * kTS + 16 * mt + g] = ex[mt][1];
+      sG[ca * kTS + 16 * mt + g + 8] = ex[mt][2];
+      sG[(ca + 1) * kTS + 16 * mt + g + 8] = ex[mt][3];
     }
-    float2 rs = mkp((ex[0][0] + ex[0][2]) + (ex[1][0] + ex[1][2]), (ex[0][1] + ex[0][3]) + (ex[1][1] + ex[1][3]));
-    float2 ra, ry = bcp(0.f);
+    __syncwarp();
+
+    // ================= contraction 2 on the numerators: Z . e^T (tensor cores) =================
     {
-      const float4 a4 = *reinterpret_cast<const float4*>(sA + ca * kTS + 4 * g);
-      const float4 b4 = *reinterpret_cast<const float4*>(sA + (ca + 1) * kTS + 4 * g);
-      ra = mkp((a4.x + a4.y) + (a4.z + a4.w), (b4.x + b4.y) + (b4.z + b4.w));
-      if (NOISY) {
-        const float4 c4 = *reinterpret_cast<const float4*>(sY + ca * kTS + 4 * g);
-        const float4 d4 = *reinterpret_cast<const float4*>(sY + (ca + 1) * kTS + 4 * g);
-        ry = mkp((c4.x + c4.y) + (c4.z + c4.w), (d4.x + d4.y) + (d4.z + d4.w));
+      uint32_t r0[4], r1[4];
+      ldsm_x4(sG + (lane & 7) * kTS + 4 * (lane >> 3), r0);
+      ldsm_x4(sG + (lane & 7) * kTS + 16 + 4 * (lane >> 3), r1);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        split_tf32(__uint_as_float(r0[m]), bh[m], bl[m]);
+        split_tf32(__uint_as_float(r1[m]), bh[4 + m], bl[4 + m]);
       }
     }
+    float cT[2][4];
 #pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      rs = add2(rs, shfl_xor2(rs, o));
-      ra = add2(ra, shfl_xor2(ra, o));
-      if (NOISY) ry = add2(ry, shfl_xor2(ry, o));
+    for (int mt = 0; mt < 2; ++mt) cT[mt][0] = cT[mt][1] = cT[mt][2] = cT[mt][3] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint4 a = sZ[(mt * 4 + c) * 32 + lane];
+        mma_tf32(cT[mt], a, bh[2 * c], bh[2 * c + 1]);
+        mma_tf32(cT[mt], a, bl[2 * c], bl[2 * c + 1]);
+      }
     }
-    float fr2[2], om2[2];
+    // ---- per-cell scalars (overlap the MMAs above): logsumexp over K, noisy class (Model.py:255-264)
+    float2 rs = mkp((ex[0][0] + ex[0][2]) + (ex[1][0] + ex[1][2]), (ex[0][1] + ex[0][3]) + (ex[1][1] + ex[1][3]));
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) rs = add2(rs, shfl_xor2(rs, o));
+    float sc2[2], fr2[2], om2[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const float mx = h ? mxb : mxa;
@@ -506,78 +541,50 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       const float fr = facc * rho;
       fr2[h] = fr;
       om2[h] = facc * omr;
+      sc2[h] = fr * rinv;                   // g_k = sc e_k = fac rho softmax_k(f)
       sfr += fr;
       sfo += om2[h];
-      const float sc = fr * rinv;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        ex[mt][h] *= sc;          // g_k = fac rho softmax_k(f)
-        ex[mt][2 + h] *= sc;
-      }
     }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
-      gW[2 * mt] += ex[mt][0] + ex[mt][1];
-      gW[2 * mt + 1] += ex[mt][2] + ex[mt][3];
-      sG[ca * kTS + 16 * mt + g] = ex[mt][0];
-      sG[(ca + 1) * kTS + 16 * mt + g] = ex[mt][1];
-      sG[ca * kTS + 16 * mt + g + 8] = ex[mt][2];
-      sG[(ca + 1) * kTS + 16 * mt + g + 8] = ex[mt][3];
+      gW[2 * mt] += fmaf(sc2[0], ex[mt][0], sc2[1] * ex[mt][1]);
+      gW[2 * mt + 1] += fmaf(sc2[0], ex[mt][2], sc2[1] * ex[mt][3]);
     }
     if (g == 0) {
       sS[ca] = fr2[0];
       sS[ca + 1] = fr2[1];
       sS[8 + ca] = om2[0];
       sS[8 + ca + 1] = om2[1];
+      sS[16 + ca] = sc2[0];
+      sS[16 + ca + 1] = sc2[1];
     }
-    __syncwarp();
-
-    // ================= contraction 2: c1^T[j, n] = Z . g^T (tensor cores) =================
-    {
-      uint32_t r0[4], r1[4];
-      ldsm_x4(sG + (lane & 7) * kTS + 4 * (lane >> 3), r0);
-      ldsm_x4(sG + (lane & 7) * kTS + 16 + 4 * (lane >> 3), r1);
+    __syncwarp();      // the A0 sums of every lane are taken: c1 may overwrite the tile
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        split_tf32(__uint_as_float(r0[m]), bh[m], bl[m]);
-        split_tf32(__uint_as_float(r1[m]), bh[4 + m], bl[4 + m]);
-      }
-    }
-    float cT[2][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) cT[mt][0] = cT[mt][1] = cT[mt][2] = cT[mt][3] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const uint4 a = sZ[(mt * 4 + c) * 32 + lane];
-        mma_tf32(cT[mt], a, bh[2 * c], bh[2 * c + 1]);
-        mma_tf32(cT[mt], a, bl[2 * c], bl[2 * c + 1]);
-      }
-    }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {     // c1 overwrites the A0 tile (its sums were taken above)
-      sA[ca * kTS + 16 * mt + g] = cT[mt][0];
-      sA[(ca + 1) * kTS + 16 * mt + g] = cT[mt][1];
-      sA[ca * kTS + 16 * mt + g + 8] = cT[mt][2];
-      sA[(ca + 1) * kTS + 16 * mt + g + 8] = cT[mt][3];
+    for (int mt = 0; mt < 2; ++mt) {
+      sA[ca * kTS + 16 * mt + g] = sc2[0] * cT[mt][0];
+      sA[(ca + 1) * kTS + 16 * mt + g] = sc2[1] * cT[mt][1];
+      sA[ca * kTS + 16 * mt + g + 8] = sc2[0] * cT[mt][2];
+      sA[(ca + 1) * kTS + 16 * mt + g + 8] = sc2[1] * cT[mt][3];
     }
 
     // ================= contraction 3: dZ[j, k] += D^T . g over the 8 cells (tensor cores) =================
+    // issued last: nothing in this tile's backward depends on it
     {
       const float4 d_lo = *reinterpret_cast<const float4*>(sD + t4 * kTS + 4 * g);        // cell t4,   markers 4g..4g+3
       const float4 d_hi = *reinterpret_cast<const float4*>(sD + (t4 + 4) * kTS + 4 * g);  // cell t4+4
-      const float4 g_lo = *reinterpret_cast<const float4*>(sG + t4 * kTS + 4 * g);        // cell t4,   features 4g..4g+3
-      const float4 g_hi = *reinterpret_cast<const float4*>(sG + (t4 + 4) * kTS + 4 * g);
+      const float4 e_lo = *reinterpret_cast<const float4*>(sG + t4 * kTS + 4 * g);        // cell t4,   features 4g..4g+3
+      const float4 e_hi = *reinterpret_cast<const float4*>(sG + (t4 + 4) * kTS + 4 * g);
+      const float sca = sS[16 + t4], scb = sS[16 + t4 + 4];
       const float dl[4] = {d_lo.x, d_lo.y, d_lo.z, d_lo.w}, dh[4] = {d_hi.x, d_hi.y, d_hi.z, d_hi.w};
-      const float gl4[4] = {g_lo.x, g_lo.y, g_lo.z, g_lo.w}, gh4[4] = {g_hi.x, g_hi.y, g_hi.z, g_hi.w};
-      uint4 ah[2], al[2];
+      const float gl4[4] = {sca * e_lo.x, sca * e_lo.y, sca * e_lo.z, sca * e_lo.w};
+      const float gh4[4] = {scb * e_hi.x, scb * e_hi.y, scb * e_hi.z, scb * e_hi.w};
+      uint4 ah[2], al2[2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {   // rows g / g+8 of m-tile mt = markers 4g+2mt / 4g+2mt+1
-        split_tf32(dl[2 * mt], ah[mt].x, al[mt].x);
-        split_tf32(dl[2 * mt + 1], ah[mt].y, al[mt].y);
-        split_tf32(dh[2 * mt], ah[mt].z, al[mt].z);
-        split_tf32(dh[2 * mt + 1], ah[mt].w, al[mt].w);
+        split_tf32(dl[2 * mt], ah[mt].x, al2[mt].x);
+        split_tf32(dl[2 * mt + 1], ah[mt].y, al2[mt].y);
+        split_tf32(dh[2 * mt], ah[mt].z, al2[mt].z);
+        split_tf32(dh[2 * mt + 1], ah[mt].w, al2[mt].w);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {   // column g of n-tile nt = feature 4g+nt
@@ -588,7 +595,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
         for (int mt = 0; mt < 2; ++mt) {
           mma_tf32(dZ[mt][nt], ah[mt], b0h, b1h);
           mma_tf32(dZ[mt][nt], ah[mt], b0l, b1l);
-          mma_tf32(dZ[mt][nt], al[mt], b0h, b1h);
+          mma_tf32(dZ[mt][nt], al2[mt], b0h, b1h);
         }
       }
     }
