@@ -162,7 +162,7 @@ def run_ours(args, w, rank, world, local_rank):
     model = cy.model.Model(y=y, priors=priors, verbose=-1, device=dev, noise='philox', seed=1,
                            N_global=N_global, row_global=[rank * n] * I, dist_group=group, **w['kw'])
     from cytofpy_b200.model.fused import FusedStep
-    fs = FusedStep(model, lr=1e-2, seed=1)       # the path cytofpy_b200.model.fit drives
+    fs = FusedStep(model, lr=1e-2, seed=1, allreduce=args.allreduce)   # the path cytofpy_b200.model.fit drives
     mb = w['mb']
     n_sampler = 0 if mb is None else I
 
@@ -274,7 +274,9 @@ def run_ours(args, w, rank, world, local_rank):
             'data': 'synthetic',
             'config': {'workload': args.workload, 'I': I, 'cells_per_gpu': I * n, 'cells_per_step_per_gpu': cells_step,
                        'J': J, 'K': w['K'], 'L': [w['L0'], w['L1']], 'minibatch': mb, 'nan_rate': w['nan'],
-                       'parallelism': 'cells sharded x%d, all-reduce of gradient block' % world,
+                       'parallelism': 'cells sharded x%d, all-reduce of gradient block (%s)' % (
+                           world, 'single GPU: none' if world == 1 else (
+                               'fused into the finalise kernel, NVLink peer stores' if fs.peers is not None else 'NCCL')),
                        'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox'},
             'e2e': {'value': cells_step * world / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms},
@@ -301,6 +303,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
+                    help='N>1: one-shot all-reduce over peer memory fused into the finalise kernel, or NCCL')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     rank = int(os.environ.get('RANK', 0))

@@ -43,6 +43,15 @@ class GlobalDesc(C.Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class PeerDesc(C.Structure):
+    """mirror of `struct cytof_peer_desc`"""
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('seq', C.c_uint64),
+                ('mailbox', C.c_void_p * MAX_PEERS)]
+
+
 _P = C.c_void_p
 _PROTOS = {
     'cytof_abi_version': (C.c_int, []),
@@ -53,6 +62,14 @@ _PROTOS = {
     'cytof_workspace_bytes': (C.c_size_t, [C.POINTER(Desc)]),
     'cytof_elbo_fwdbwd_f32': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'cytof_elbo_fwdbwd_packed': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'cytof_peer_mailbox_bytes': (C.c_size_t, [C.POINTER(Desc), C.c_int32]),
+    'cytof_peer_alloc': (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    'cytof_peer_free': (C.c_int, [_P]),
+    'cytof_ipc_get_handle': (C.c_int, [_P, C.c_char_p]),
+    'cytof_ipc_open_handle': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'cytof_ipc_close': (C.c_int, [_P]),
+    'cytof_elbo_fwdbwd_allreduce': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
+                                              C.POINTER(PeerDesc), _P]),
     'cytof_global_sizes': (C.c_int, [C.POINTER(GlobalDesc), C.POINTER(C.c_int64)]),
     'cytof_global_fwd_f64': (C.c_int, [C.POINTER(GlobalDesc), _P, _P, _P, _P, _P, _P, _P]),
     'cytof_global_bwd_adam_f64': (C.c_int, [C.POINTER(GlobalDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

@@ -12,7 +12,8 @@ size_t workspace_bytes(const cytof_desc* d);
 int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
                   double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
-                  cudaError_t* err);
+                  cudaError_t* err, const cytof_peer_desc* peer = nullptr);
+size_t peer_mailbox_bytes(const cytof_desc* d, int world);
 int launch_labels(const cytof_desc* d, const float* y, const float* globals, const uint64_t* zmask,
                   int32_t* lam_out, float* probs_out, cudaStream_t stream, cudaError_t* err);
 struct GlobalParams;
@@ -156,6 +157,66 @@ int cytof_elbo_fwdbwd_packed(const cytof_desc* d, const float* y, const int32_t*
   cudaError_t err = cudaSuccess;
   rc = launch_fwdbwd(d, y, idx, eps, globals, zmask, nullptr, nullptr, packed, workspace, workspace_bytes_,
                      (cudaStream_t)stream, &err);
+  if (rc == CYTOF_ECUDA) set_cuda_err(err);
+  return rc;
+}
+
+size_t cytof_peer_mailbox_bytes(const cytof_desc* d, int32_t world) {
+  if (validate_desc(d) != CYTOF_OK || world < 1 || world > CYTOF_MAX_PEERS) return 0;
+  return peer_mailbox_bytes(d, world);
+}
+int cytof_peer_alloc(size_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return CYTOF_EINVAL;
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
+int cytof_peer_free(void* ptr) {
+  const cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
+int cytof_ipc_get_handle(void* ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!ptr || !handle) return CYTOF_EINVAL;
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
+  memcpy(handle, &h, 64);
+  return CYTOF_OK;
+}
+int cytof_ipc_open_handle(const unsigned char handle[64], void** ptr) {
+  if (!ptr || !handle) return CYTOF_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
+int cytof_ipc_close(void* ptr) {
+  const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
+int cytof_elbo_fwdbwd_allreduce(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                                const float* globals, const uint64_t* zmask, double* packed,
+                                void* workspace, size_t workspace_bytes_, const cytof_peer_desc* peer,
+                                void* stream) {
+  int rc = validate_desc(d);
+  if (rc != CYTOF_OK) return rc;
+  if (!globals || !zmask || !packed || !workspace || !peer) return CYTOF_EINVAL;
+  if (!y && d->cell_begin[d->I] > 0) return CYTOF_EINVAL;
+  if (peer->world < 1 || peer->world > CYTOF_MAX_PEERS || peer->rank < 0 || peer->rank >= peer->world ||
+      peer->seq == 0)
+    return CYTOF_EINVAL;
+  for (int q = 0; q < peer->world; ++q)
+    if (peer->world > 1 && !peer->mailbox[q]) return CYTOF_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(packed) & 7) || (reinterpret_cast<uintptr_t>(zmask) & 7)) return CYTOF_EALIGN;
+  cudaError_t err = cudaSuccess;
+  rc = launch_fwdbwd(d, y, idx, eps, globals, zmask, nullptr, nullptr, packed, workspace, workspace_bytes_,
+                     (cudaStream_t)stream, &err, peer);
   if (rc == CYTOF_ECUDA) set_cuda_err(err);
   return rc;
 }

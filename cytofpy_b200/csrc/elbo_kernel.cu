@@ -17,6 +17,8 @@
 // fp64 per warp; per-CTA partial sums are combined in a fixed order in shared memory, and
 // the finalise kernel sums the per-CTA records in fp64 in a fixed order => bitwise
 // reproducible results for a given grid.
+#include <string.h>
+
 #include "common.cuh"
 #include "elbo_kernel_j32.cuh"
 #include "elbo_kernel_mma.cuh"
@@ -444,15 +446,44 @@ elbo_fwdbwd_kernel(const ElboParams p) {
 // records s, s + kFinLanes, ... of the relevant sample(s) in fp64, the lanes are combined by a
 // fixed butterfly (=> reproducible for a given grid), then the per-sample scalings are applied.
 constexpr int kFinLanes = 8;
+
+// One-shot all-reduce over NVLink / NVSwitch peer memory, fused into the finalise kernel.  Every
+// rank owns a mailbox (cudaMalloc'ed by cytof_peer_alloc, mapped into the peers with CUDA IPC):
+//   [0, 128)    uint64 flags[src]: sequence number of the last step rank `src` has delivered
+//   [128, 132)  uint32 ticket: CTAs of the local finalise kernel that are done (local use)
+//   [132, 136)  uint32 error: set when a wait timed out
+//   [256, ...)  double slots[parity][src][nout]: the packed vector of rank `src` for steps of that parity
+// Step s: every finalise thread stores its output straight into slot [s & 1][rank] of EVERY mailbox
+// (its own included); the last CTA of the grid publishes flags[rank] = s to every peer with a
+// system-scope release, waits (acquire, bounded) until all its own flags reach s and sums the
+// world slots in rank order -- the same order on every rank, so the replicas stay bit-identical.
+// Two parities suffice: no rank can start step s + 2 before every rank has finished reading step s.
+struct PeerArgs {
+  int world, rank;
+  unsigned long long seq;
+  int nout;
+  unsigned char* mailbox[CYTOF_MAX_PEERS];
+};
+constexpr size_t kPeerHeaderBytes = 256;
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
-                                     double* __restrict__ ll_lqy, double* __restrict__ packed) {
+                                     double* __restrict__ ll_lqy, double* __restrict__ packed,
+                                     const PeerArgs peer) {
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const PartialLayout pl = partial_layout(J, K, L0, L1);
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = gt / kFinLanes, sub = gt % kFinLanes;
-  if (t >= bl.total + 2) return;      // whole lane groups leave together
+  const bool live = t < bl.total + 2;      // whole lane groups are live or not together
   const unsigned gmask = ((1u << kFinLanes) - 1u) << ((threadIdx.x & 31) / kFinLanes * kFinLanes);
   const float* __restrict__ P = p.partials;
   const float* __restrict__ G = p.globals;
@@ -476,20 +507,15 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     return group_sum(a);
   };
   auto sum_sample = [&](int i, int off) -> double { return sum_range(p.blk_begin[i], p.blk_begin[i + 1], off); };
-  if (t >= bl.total) {  // ll, log_qy
+  double r = 0.0;
+  if (!live) {
+  } else if (t >= bl.total) {  // ll, log_qy
     const int which = t - bl.total;
     double a = 0.0;
     for (int b = sub; b < p.nblocks; b += kFinLanes)
       a += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
-    a = group_sum(a);
-    if (sub == 0) {
-      if (ll_lqy) ll_lqy[which] = a;
-      if (packed) packed[t] = a;
-    }
-    return;
-  }
-  double r = 0.0;
-  if (t < bl.dmu1) {  // dmu0[l] = sum_i (1/sig_i^2) sum w d
+    r = group_sum(a);
+  } else if (t < bl.dmu1) {  // dmu0[l] = sum_i (1/sig_i^2) sum w d
     const int l = t - bl.dmu0;
     for (int i = 0; i < I; ++i) {
       const double s = (double)G[gl.sig + i];
@@ -531,9 +557,51 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     const int q = t - bl.dlq, i = q / J, j = q % J;
     r = -(double)p.fac[i] * (double)p.scale * sum_sample(i, pl.nm + j);
   }
-  if (sub == 0) {
-    if (grad_block) grad_block[t] = (float)r;
-    if (packed) packed[t] = r;
+  if (peer.world <= 1) {
+    if (live && sub == 0) {
+      if (t >= bl.total) {
+        if (ll_lqy) ll_lqy[t - bl.total] = r;
+      } else if (grad_block) {
+        grad_block[t] = (float)r;
+      }
+      if (packed) packed[t] = r;
+    }
+    return;
+  }
+  // ---- fused one-shot all-reduce (see PeerArgs)
+  const int par = (int)(peer.seq & 1ull);
+  const size_t slot_off = kPeerHeaderBytes + ((size_t)par * peer.world + peer.rank) * (size_t)peer.nout * sizeof(double);
+  if (live) {     // the 8 lanes of an output share the peers between them
+    for (int q = sub; q < peer.world; q += kFinLanes)
+      reinterpret_cast<double*>(peer.mailbox[q] + slot_off)[t] = r;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  unsigned char* mine = peer.mailbox[peer.rank];
+  unsigned* ticket = reinterpret_cast<unsigned*>(mine + 128);
+  unsigned* errw = reinterpret_cast<unsigned*>(mine + 132);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < peer.world) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    st_release_sys(reinterpret_cast<unsigned long long*>(peer.mailbox[threadIdx.x]) + peer.rank, peer.seq);
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < peer.seq) {
+      if (clock64() - t0 > 4000000000ll) { *errw = 1u; break; }    // ~2 s: a peer died; never hang the GPU
+    }
+  }
+  __syncthreads();
+  const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u;
+  const double* slots = reinterpret_cast<const double*>(mine + kPeerHeaderBytes) + (size_t)par * peer.world * peer.nout;
+  for (int o = threadIdx.x; o < peer.nout; o += blockDim.x) {
+    double a = 0.0;
+    for (int q = 0; q < peer.world; ++q) a += __ldcg(slots + (size_t)q * peer.nout + o);
+    if (bad) a = __longlong_as_double(0x7ff8000000000000ll);
+    packed[o] = a;
   }
 }
 
@@ -745,10 +813,15 @@ size_t workspace_bytes(const cytof_desc* d) {
   return sizeof(float) * (size_t)pl.total * (size_t)max_grid_blocks() + 256;
 }
 
+size_t peer_mailbox_bytes(const cytof_desc* d, int world) {
+  const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
+  return kPeerHeaderBytes + (size_t)2 * world * (bl.total + 2) * sizeof(double);
+}
+
 int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
                   double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
-                  cudaError_t* err) {
+                  cudaError_t* err, const cytof_peer_desc* peer) {
   const Variant* v = pick_variant(d->J, d->K, d->L0, d->L1);
   ElboParams p;
   fill_params(d, &p);
@@ -771,7 +844,17 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     if (*err != cudaSuccess) return CYTOF_ECUDA;
   }
   const int nout = bl.total + 2;
-  elbo_finalize_kernel<<<(nout * kFinLanes + 127) / 128, 128, 0, stream>>>(p, grad_block, ll_lqy, packed);
+  PeerArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.world = 1;
+  if (peer && peer->world > 1) {
+    pa.world = peer->world;
+    pa.rank = peer->rank;
+    pa.seq = peer->seq;
+    pa.nout = nout;
+    for (int q = 0; q < peer->world; ++q) pa.mailbox[q] = static_cast<unsigned char*>(peer->mailbox[q]);
+  }
+  elbo_finalize_kernel<<<(nout * kFinLanes + 255) / 256, 256, 0, stream>>>(p, grad_block, ll_lqy, packed, pa);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }

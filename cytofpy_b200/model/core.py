@@ -135,7 +135,8 @@ class Model(torch.nn.Module):
         key = tuple(batch.counts)
         hit = self._counts_cache.get(key)
         if hit is None:      # counts are static per (minibatch size, shard): one collective, once
-            t = torch.tensor(batch.counts, dtype=torch.int64, device=self.device)
+            on_cpu = torch.distributed.get_backend(self.dist_group) == 'gloo'
+            t = torch.tensor(batch.counts, dtype=torch.int64, device='cpu' if on_cpu else self.device)
             torch.distributed.all_reduce(t, group=self.dist_group)
             hit = self._counts_cache[key] = [int(v) for v in t.tolist()]
         return hit

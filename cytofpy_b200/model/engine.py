@@ -127,6 +127,24 @@ class CellEngine:
         self.launches += 2
         return self.grad_block, self.ll_lqy
 
+    def full_batch(self):
+        return Batch(self.N_local)
+
+    def fwdbwd_allreduce(self, batch, globals_f32, zmask_i64, packed_f64, counts_global, peers):
+        """fwdbwd_packed with the sum over ranks fused into the finalise kernel (peer-memory
+        mailboxes, model/peer.py): `packed_f64` receives the all-reduced vector; no NCCL call."""
+        d = self._desc(batch)
+        self.set_fac(d, batch, counts_global)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.cytof_elbo_fwdbwd_allreduce(
+                C.byref(d), _ptr(self.y_dev), _ptr(batch.idx), _ptr(batch.eps), _ptr(globals_f32),
+                _ptr(zmask_i64), _ptr(packed_f64), _ptr(self.workspace), C.c_size_t(self.ws_bytes),
+                C.byref(peers.next()), C.c_void_p(stream))
+        _lib.check(rc)
+        self.launches += 2
+        return packed_f64
+
     def fwdbwd_packed(self, batch, globals_f32, zmask_i64, packed_f64, counts_global=None):
         """Same as fwdbwd, results as one fp64 vector [grad block | ll | log_qy] in `packed_f64`."""
         d = self._desc(batch)

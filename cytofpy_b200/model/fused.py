@@ -62,7 +62,7 @@ def recognise_priors(priors, model_noisy):
 
 
 class FusedStep:
-    def __init__(self, model, lr=1e-1, betas=(0.9, 0.999), adam_eps=1e-8, seed=0):
+    def __init__(self, model, lr=1e-1, betas=(0.9, 0.999), adam_eps=1e-8, seed=0, allreduce='peer'):
         hyp = recognise_priors(model.priors, model.model_noisy)
         if hyp is None:
             raise ValueError('priors outside the families the fused global kernels implement')
@@ -105,6 +105,12 @@ class FusedStep:
         self.step_dev = z(1, torch.int64)
         self.t = 0
         self.launches = 0
+        # multi-GPU: 'peer' (default) = one-shot all-reduce over peer memory fused into the finalise
+        # kernel; 'nccl' = separate torch.distributed all-reduce (kept for A/B measurements)
+        self.peers = None
+        if model.dist_group is not None and allreduce == 'peer':
+            from .peer import PeerMailboxes
+            self.peers = PeerMailboxes(self.eng, model.dist_group)
         self._bind()
 
     def _bind(self):
@@ -145,9 +151,13 @@ class FusedStep:
             _lib.check(self.lib.cytof_global_fwd_f64(
                 C.byref(g), _ptr(self.theta), _ptr(global_noise), _ptr(self.stash), _ptr(self.globals),
                 _ptr(self.zmask), _ptr(self.scalars_in), stream))
-        eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, m._counts_global(batch))
-        if m.dist_group is not None:
-            torch.distributed.all_reduce(self.packed, group=m.dist_group)
+        if self.peers is not None:      # sum over ranks fused into the finalise kernel (NVLink P2P)
+            eng.fwdbwd_allreduce(batch, self.globals, self.zmask, self.packed, m._counts_global(batch),
+                                 self.peers)
+        else:
+            eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, m._counts_global(batch))
+            if m.dist_group is not None:
+                torch.distributed.all_reduce(self.packed, group=m.dist_group)
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.cytof_global_bwd_adam_f64(
                 C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),

@@ -107,6 +107,37 @@ int cytof_elbo_fwdbwd_packed(const cytof_desc* d, const float* y, const int32_t*
                              const float* globals, const uint64_t* zmask, double* packed,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- multi-GPU: the step's only exchange, fused into the finalise kernel -------------------
+ * The reference has no communication at all; with cells sharded over the GPUs of one
+ * node the packed vector [grad block | ll | log_qy] must be summed over ranks between the per-cell
+ * kernel and the backward of the global part.  Instead of a separate NCCL all-reduce the finalise
+ * kernel stores its outputs directly into a mailbox of every peer (NVLink / NVSwitch P2P stores
+ * through CUDA-IPC mappings), publishes a sequence flag and sums the `world` slots in rank order.
+ *   cytof_peer_mailbox_bytes  size of one rank's mailbox
+ *   cytof_peer_alloc/free     cudaMalloc'ed, zeroed mailbox (the one exception to "never allocates":
+ *                             IPC handles need a whole allocation, not a caching-allocator slice)
+ *   cytof_ipc_get_handle      64-byte cudaIpcMemHandle_t of a mailbox, to be sent to the peers
+ *   cytof_ipc_open_handle     maps a peer's mailbox (enables peer access lazily); cytof_ipc_close
+ *   cytof_elbo_fwdbwd_allreduce   = cytof_elbo_fwdbwd_packed, but `packed` receives the SUM over
+ *                             ranks; peer->seq must be 1, 2, 3, ... on every rank in lock step.
+ * A wait that exceeds ~2 s (a dead peer) fills `packed` with NaN instead of hanging the GPU. */
+#define CYTOF_MAX_PEERS 16
+typedef struct cytof_peer_desc {
+  int32_t world, rank;
+  uint64_t seq;
+  void* mailbox[CYTOF_MAX_PEERS]; /* [rank] = own allocation, others = IPC mappings */
+} cytof_peer_desc;
+size_t cytof_peer_mailbox_bytes(const cytof_desc* d, int32_t world);
+int cytof_peer_alloc(size_t bytes, void** ptr);
+int cytof_peer_free(void* ptr);
+int cytof_ipc_get_handle(void* ptr, unsigned char handle[64]);
+int cytof_ipc_open_handle(const unsigned char handle[64], void** ptr);
+int cytof_ipc_close(void* ptr);
+int cytof_elbo_fwdbwd_allreduce(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
+                                const float* globals, const uint64_t* zmask, double* packed,
+                                void* workspace, size_t workspace_bytes, const cytof_peer_desc* peer,
+                                void* stream);
+
 /* Writes the imputed minibatch y_out[C, J] (vae.py:33) for the same descriptor/noise. */
 int cytof_impute_emit_f32(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                           const float* globals, float* y_out, void* stream);
