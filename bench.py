@@ -36,6 +36,18 @@ WORKLOADS = {
     'cfg4': dict(I=8, n=125000, J=32, K=30, L0=5, L1=5, mb=None, nan=0.0, kw={}),
     'cfg5': dict(I=8, n=1250000, J=40, K=50, L0=8, L1=8, mb=None, nan=0.0, kw={}),
 }
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 METRIC = 'ELBO fwd+bwd cells/sec (J=32,K=30,L=5)'
 UNIT = 'cells/s'
 L2_FLUSH_BYTES = 512 << 20
@@ -131,14 +143,14 @@ def run_reference(args, w, rank, world):
     sample = 'oracle port of reference update (fp64 torch CPU, autograd, Adam) on %d cells/step ' \
              '(%d samples x %d%s) at the workload J/K/L' % (cells, w['I'], per,
                                                            '' if w['mb'] is None else ', minibatch %d' % w['mb'])
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': args.workload, 'I': w['I'], 'J': w['J'], 'K': w['K'], 'L': [w['L0'], w['L1']]},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 def run_ours(args, w, rank, world, local_rank):
@@ -167,7 +179,12 @@ def run_ours(args, w, rank, world, local_rank):
     n_sampler = 0 if mb is None else I
 
     def one_step(t):
-        return fs.step(draw_idx(t))
+        # after the first (host-driven) warm-up step the whole step is ONE CUDA-graph replay
+        if t == 0:
+            return fs.step(draw_idx(t))
+        if getattr(fs, 'graph', None) is None:
+            fs.capture(mb)
+        return fs.graph_step()
 
     def draw_idx(t):
         return [range(n)] * I if mb is None else cy.model.device_minibatch(model, mb, t, 1)
@@ -199,8 +216,9 @@ def run_ours(args, w, rank, world, local_rank):
     barrier()
     sampler.stop_flag = True
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    launches = fs.launches - launches0 + n_sampler * args.steps
+    launches = fs.launches - launches0      # graph_step counts the sampler kernels itself
 
+    fs.release_graph()
     # ---- dominant kernel alone (CUDA events on the launching stream, L2 flushed)
     model._step += 1
     with torch.no_grad():
@@ -277,7 +295,8 @@ def run_ours(args, w, rank, world, local_rank):
                        'parallelism': 'cells sharded x%d, all-reduce of gradient block (%s)' % (
                            world, 'single GPU: none' if world == 1 else (
                                'fused into the finalise kernel, NVLink peer stores' if fs.peers is not None else 'NCCL')),
-                       'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox'},
+                       'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox',
+                       'step': 'one CUDA-graph replay (device sampler, global fwd, per-cell kernel, finalise, global bwd + Adam)'},
             'e2e': {'value': cells_step * world / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms},
             'gpu_launches': int(launches),
@@ -290,12 +309,18 @@ def run_ours(args, w, rank, world, local_rank):
                          'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
             'cpu_baseline': cpu,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner)
+    # are sent to stderr for the whole run; the JSON goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -24,6 +24,7 @@ class Desc(C.Structure):
         ('row_base', C.c_int64 * MAX_SAMPLES),
         ('row_global', C.c_int64 * MAX_SAMPLES),
         ('fac', C.c_double * MAX_SAMPLES),
+        ('step_dev', C.c_void_p),
     ]
 
 
@@ -40,6 +41,7 @@ class GlobalDesc(C.Structure):
         ('seed', C.c_uint64), ('step', C.c_uint64),
         ('grad_scale', C.c_double), ('lr', C.c_double), ('beta1', C.c_double), ('beta2', C.c_double),
         ('adam_eps', C.c_double), ('adam_step', C.c_int64),
+        ('step_dev', C.c_void_p),
     ]
 
 
@@ -49,7 +51,7 @@ MAX_PEERS = 16
 class PeerDesc(C.Structure):
     """mirror of `struct cytof_peer_desc`"""
     _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('seq', C.c_uint64),
-                ('mailbox', C.c_void_p * MAX_PEERS)]
+                ('mailbox', C.c_void_p * MAX_PEERS), ('seq_dev', C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -80,6 +82,7 @@ _PROTOS = {
     'cytof_adam_step_f64': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.c_double, C.c_int64, _P, _P, _P]),
     'cytof_sample_minibatch': (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
+    'cytof_sample_minibatch_dev': (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, _P, C.c_int32, _P, _P]),
 }
 EXPORTS = tuple(_PROTOS)
 
@@ -105,7 +108,7 @@ def load():
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.cytof_abi_version() != 1:
+    if lib.cytof_abi_version() != 2:
         raise RuntimeError('cytofpy_b200: ABI version mismatch')
     _lib = lib
     return lib

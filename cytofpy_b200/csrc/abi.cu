@@ -59,10 +59,20 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
+__host__ __device__ inline unsigned long long sampler_key(unsigned long long seed, unsigned long long step, int sample) {
+  // splitmix64 of (seed, step, sample) -> Feistel key
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(sample + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
 __global__ void sample_minibatch_kernel(long long N, long long m, unsigned long long key, int hbits,
-                                        int32_t* __restrict__ out) {
+                                        int32_t* __restrict__ out, unsigned long long seed,
+                                        const long long* __restrict__ step_dev, int sample) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
+  if (step_dev) key = sampler_key(seed, (unsigned long long)(*step_dev + 1), sample);
   const uint32_t hmask = (1u << hbits) - 1u;
   const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
   unsigned long long x = (unsigned long long)t;
@@ -299,8 +309,8 @@ int cytof_adam_step_f64(double* param, const double* grad, double* exp_avg, doub
   return CYTOF_OK;
 }
 
-int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
-                           int32_t* idx_out, void* stream) {
+static int sample_minibatch_impl(int64_t N, int64_t m, uint64_t seed, uint64_t step, const int64_t* step_dev,
+                                 int32_t sample, int32_t* idx_out, void* stream) {
   if (!idx_out || N < 0 || m < 0 || N > 0x7fffffffLL) return CYTOF_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   if (N == 0 || m == 0) return CYTOF_OK;
@@ -311,16 +321,23 @@ int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, i
     while ((1LL << bits) < N) ++bits;
     int hbits = (bits + 1) / 2;
     if (hbits < 1) hbits = 1;
-    // splitmix64 of (seed, step, sample) -> Feistel key
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(sample + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    sample_minibatch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(N, m, z, hbits, idx_out);
+    const unsigned long long z = sampler_key(seed, step, sample);
+    sample_minibatch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(
+        N, m, z, hbits, idx_out, seed, reinterpret_cast<const long long*>(step_dev), sample);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_cuda_err(err); return CYTOF_ECUDA; }
   return CYTOF_OK;
+}
+
+int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
+                           int32_t* idx_out, void* stream) {
+  return sample_minibatch_impl(N, m, seed, step, nullptr, sample, idx_out, stream);
+}
+int cytof_sample_minibatch_dev(int64_t N, int64_t m, uint64_t seed, const int64_t* step_dev,
+                               int32_t sample, int32_t* idx_out, void* stream) {
+  if (!step_dev) return CYTOF_EINVAL;
+  return sample_minibatch_impl(N, m, seed, 0, step_dev, sample, idx_out, stream);
 }
 
 }  // extern "C"

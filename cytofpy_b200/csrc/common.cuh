@@ -82,15 +82,31 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
   }
 }
 
-// One standard-normal draw for (global row, marker j) of step `step` (Box-Muller on two
-// Philox words).  Independent of how cells are split over warps, CTAs or GPUs.
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t step, uint64_t grow, uint32_t j) {
-  uint32_t c[4] = {(uint32_t)grow, (uint32_t)(grow >> 32), j, step};
+// Standard-normal draws for (global row, marker j) of step `step`.  One Philox4x32-10 block is
+// keyed by (global row / 4, marker) and yields FOUR normals (two Box-Muller pairs), one for each
+// of the 4 consecutive rows of the group: a warp that walks consecutive rows (full-batch tiles)
+// pays one Philox block per 4 cells.  Independent of how cells are split over warps, CTAs or GPUs.
+__device__ __forceinline__ float philox_unit(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uint64_t grp, uint32_t j, float out[4]) {
+  uint32_t c[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), j, step};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float r = sqrtf(-2.0f * kLn2 * fast_lg2(u1));
-  return r * __cosf(6.283185307179586f * u2);
+  const float r0 = sqrtf(-2.0f * kLn2 * fast_lg2(philox_unit(c[0])));
+  const float r1 = sqrtf(-2.0f * kLn2 * fast_lg2(philox_unit(c[2])));
+  const float a0 = 6.283185307179586f * philox_unit(c[1]), a1 = 6.283185307179586f * philox_unit(c[3]);
+  out[0] = r0 * __cosf(a0);
+  out[1] = r0 * __sinf(a0);
+  out[2] = r1 * __cosf(a1);
+  out[3] = r1 * __sinf(a1);
+}
+// the draw of one (row, marker): the same values as philox_normal4, only the needed one evaluated
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t step, uint64_t grow, uint32_t j) {
+  const uint64_t grp = grow >> 2;
+  uint32_t c[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), j, step};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const bool second = (grow & 2ull) != 0ull;
+  const float r = sqrtf(-2.0f * kLn2 * fast_lg2(philox_unit(second ? c[2] : c[0])));
+  const float a = 6.283185307179586f * philox_unit(second ? c[3] : c[1]);
+  return r * ((grow & 1ull) ? __sinf(a) : __cosf(a));
 }
 
 // Offsets (in floats) of the sections of `globals` (include/cytof_b200.h).
@@ -175,6 +191,7 @@ struct ElboParams {
   float noisy_sd, scale;
   unsigned long long seed;
   uint32_t step;
+  const long long* step_dev;   // non-null: the step is *step_dev + 1 (CUDA-graph replay)
   int nblocks;
   long long cell_begin[CYTOF_MAX_SAMPLES + 1];
   long long row_base[CYTOF_MAX_SAMPLES];
@@ -182,5 +199,9 @@ struct ElboParams {
   float fac[CYTOF_MAX_SAMPLES];
   int blk_begin[CYTOF_MAX_SAMPLES + 1];
 };
+
+__device__ __forceinline__ uint32_t elbo_step(const ElboParams& p) {
+  return p.step_dev ? (uint32_t)(*p.step_dev + 1) : p.step;
+}
 
 }  // namespace cytof

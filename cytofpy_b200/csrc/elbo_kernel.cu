@@ -198,7 +198,7 @@ elbo_fwdbwd_kernel(const ElboParams p) {
           const int j = lane + 32 * jp;
           e[jp] = p.noise_mode == CYTOF_NOISE_EXTERNAL
                       ? (p.eps ? __ldg(p.eps + (cb + c) * J + j) : 0.f)
-                      : philox_normal(p.seed, p.step, grow_base + (unsigned long long)(row_cur - row_base), j);
+                      : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)(row_cur - row_base), j);
           yv[jp] = fmaf(sd[jp], e[jp], vm[jp]);
         }
     }
@@ -461,6 +461,7 @@ constexpr int kFinLanes = 8;
 struct PeerArgs {
   int world, rank;
   unsigned long long seq;
+  const long long* seq_dev;    // non-null: seq = *seq_dev + 1
   int nout;
   unsigned char* mailbox[CYTOF_MAX_PEERS];
 };
@@ -569,7 +570,8 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     return;
   }
   // ---- fused one-shot all-reduce (see PeerArgs)
-  const int par = (int)(peer.seq & 1ull);
+  const unsigned long long seq = peer.seq_dev ? (unsigned long long)(*peer.seq_dev + 1) : peer.seq;
+  const int par = (int)(seq & 1ull);
   const size_t slot_off = kPeerHeaderBytes + ((size_t)par * peer.world + peer.rank) * (size_t)peer.nout * sizeof(double);
   if (live) {     // the 8 lanes of an output share the peers between them
     for (int q = sub; q < peer.world; q += kFinLanes)
@@ -587,10 +589,10 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   __threadfence_system();
   if ((int)threadIdx.x < peer.world) {
     if (threadIdx.x == 0) *ticket = 0u;
-    st_release_sys(reinterpret_cast<unsigned long long*>(peer.mailbox[threadIdx.x]) + peer.rank, peer.seq);
+    st_release_sys(reinterpret_cast<unsigned long long*>(peer.mailbox[threadIdx.x]) + peer.rank, seq);
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + threadIdx.x;
     const long long t0 = clock64();
-    while (ld_acquire_sys(f) < peer.seq) {
+    while (ld_acquire_sys(f) < seq) {
       if (clock64() - t0 > 4000000000ll) { *errw = 1u; break; }    // ~2 s: a peer died; never hang the GPU
     }
   }
@@ -620,7 +622,7 @@ __global__ void impute_emit_kernel(const ElboParams p, float* __restrict__ eps_o
   if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
     if (p.eps) e = p.eps[c * p.J + j];
   } else {
-    e = philox_normal(p.seed, p.step, (unsigned long long)(p.row_global[i] + lrow), j);
+    e = philox_normal(p.seed, elbo_step(p), (unsigned long long)(p.row_global[i] + lrow), j);
   }
   if (eps_out) { eps_out[t] = e; return; }
   const GlobalsLayout gl = globals_layout(p.I, p.J, p.K, p.L0, p.L1);
@@ -763,6 +765,7 @@ void fill_params(const cytof_desc* d, ElboParams* p) {
   p->scale = d->scale;
   p->seed = d->seed;
   p->step = (uint32_t)d->step;
+  p->step_dev = reinterpret_cast<const long long*>(d->step_dev);
   for (int i = 0; i <= d->I; ++i) p->cell_begin[i] = d->cell_begin[i];
   for (int i = 0; i < d->I; ++i) {
     p->row_base[i] = d->row_base[i];
@@ -851,6 +854,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     pa.world = peer->world;
     pa.rank = peer->rank;
     pa.seq = peer->seq;
+    pa.seq_dev = reinterpret_cast<const long long*>(peer->seq_dev);
     pa.nout = nout;
     for (int q = 0; q < peer->world; ++q) pa.mailbox[q] = static_cast<unsigned char*>(peer->mailbox[q]);
   }

@@ -35,6 +35,7 @@ struct GlobalParams {
   // normalising constants of the priors (pure functions of the hyper-parameters: host lgamma)
   double n_delta0, n_delta1, n_sig2, n_alpha, n_eps, n_eta0, n_eta1, n_W;
   unsigned long long seed, step;
+  const long long* step_dev;   // non-null: step = *step_dev + 1 (CUDA-graph replay)
   // real-vector layout: offset of each block in the R-vector (noise / reals) and in theta
   int roff[B_COUNT + 1];   // roff[b]..roff[b+1]
   int toff[B_COUNT];       // theta offset of m; log_s at toff + size
@@ -116,7 +117,7 @@ global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, c
     double loc, sc;
     if (squashed(b)) { loc = 20.0 * sigmoid_d(m) - 10.0; sc = 10.0 * sigmoid_d(ls); }
     else { loc = m; sc = exp(ls); }
-    const double e = p.noise_mode == CYTOF_NOISE_EXTERNAL ? eps_in[q] : philox_normal_d(p.seed, p.step, (unsigned)q);
+    const double e = p.noise_mode == CYTOF_NOISE_EXTERNAL ? eps_in[q] : philox_normal_d(p.seed, p.step_dev ? (unsigned long long)(*p.step_dev + 1) : p.step, (unsigned)q);
     const double r = loc + e * sc;
     real[q] = r;
     eps_out[q] = e;
@@ -481,6 +482,7 @@ int global_make_params(const cytof_global_desc* g, GlobalParams* p) {
     p->n_W = lgamma(sw) - lw;
   }
   p->seed = g->seed; p->step = g->step;
+  p->step_dev = reinterpret_cast<const long long*>(g->step_dev);
   p->grad_scale = g->grad_scale; p->lr = g->lr; p->beta1 = g->beta1; p->beta2 = g->beta2; p->adam_eps = g->adam_eps;
   p->step_host = g->adam_step;
   fill_layout(p);

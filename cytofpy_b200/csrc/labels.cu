@@ -76,7 +76,7 @@ label_sample_kernel(const ElboParams p, const float* __restrict__ y, int32_t* __
       for (int t = lane; t <= K; t += 32) probs_out[c * (K + 1) + t] = sP[t];
     if (lane == 0) {   // inverse-CDF draw, u keyed by (seed, step, global row)
       uint32_t ctr[4] = {(uint32_t)(p.row_global[i] + (c - p.cell_begin[i])), (uint32_t)((unsigned long long)(p.row_global[i] + (c - p.cell_begin[i])) >> 32),
-                         0x1ab31u + (uint32_t)i, p.step};
+                         0x1ab31u + (uint32_t)i, elbo_step(p)};
       philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
       const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
       float cdf = 0.f;

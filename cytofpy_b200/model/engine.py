@@ -36,6 +36,7 @@ class CellEngine:
         holds.  N_global: per-sample global cell counts (defaults to the local ones);
         row_global: global id of the first local row of each sample (multi-GPU sharding)."""
         self.lib = _lib.load()
+        self.step_dev = None      # device pointer of a step counter (CUDA-graph replay), or None
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('cytofpy_b200: the ELBO hot path needs a CUDA device (got %s); '
@@ -78,6 +79,7 @@ class CellEngine:
         d.noisy_sd, d.scale = self.noisy_sd, self.scale
         d.flags = _lib.FLAG_NO_MISSING if self.no_missing else 0
         d.seed, d.step = self.seed & (2 ** 64 - 1), batch.step
+        d.step_dev = self.step_dev
         cb = 0
         for i in range(self.I):
             d.cell_begin[i] = cb

@@ -12,6 +12,7 @@ in ONE flat fp64 device buffer `theta`; the Parameters of `model.mp[key].vp` and
 """
 import ctypes as C
 
+import numpy as np
 import torch
 from torch.distributions import Beta, Dirichlet, Gamma, Uniform
 from torch.distributions.log_normal import LogNormal
@@ -165,6 +166,82 @@ class FusedStep:
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
         self.launches += 8      # global fwd (2) + per-cell (2) + global bwd / Adam (4)
         return self.scalars
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, minibatch_size=None):
+        """Capture one whole training step -- device minibatch sampler, global forward, fused
+        per-cell kernel + finalise (+ all-reduce), global backward + Adam -- in ONE CUDA graph.
+        All step-dependent inputs (Philox counters of the global and per-cell noise, sampler key,
+        Adam step, peer sequence number) are read on the device from `step_dev`, which the last
+        kernel of the step bumps, so `graph_step()` is a bare replay (reference fit.py:91-106)."""
+        m, eng, g = self.model, self.eng, self.g
+        I = eng.I
+        counts = [n if (minibatch_size is None or minibatch_size >= n) else int(minibatch_size)
+                  for n in eng.N_local]
+        full = all(c == n for c, n in zip(counts, eng.N_local))
+        if self.t == 0:      # one ordinary step first: module loading / attribute calls stay out of the capture
+            from .train import device_minibatch
+            self.step([range(n) for n in eng.N_local] if full else
+                      device_minibatch(m, minibatch_size, 0, self.g.seed))
+        idx_buf = None if full else torch.empty(sum(counts), dtype=torch.int32, device=self.dev)
+        batch = Batch(counts, idx_buf, None, step=0)
+        cg = m._counts_global(batch)                     # (cached) collective outside the capture
+        self.step_dev.fill_(self.t)
+        sd = self.step_dev.data_ptr()
+        g.step_dev, eng.step_dev, g.noise_mode = sd, sd, _lib.NOISE_PHILOX
+        if self.peers is not None:
+            assert self.peers.seq == self.t, 'peer sequence and step count must run in lock step'
+            self.peers.desc.seq_dev = sd
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        seed = C.c_uint64(self.g.seed)
+
+        def body():
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            with torch.cuda.device(self.dev):
+                if idx_buf is not None:
+                    for i in range(I):
+                        _lib.check(self.lib.cytof_sample_minibatch_dev(
+                            C.c_int64(eng.N_local[i]), C.c_int64(counts[i]), seed, C.c_void_p(sd), C.c_int32(i),
+                            C.c_void_p(idx_buf.data_ptr() + 4 * int(offs[i])), stream))
+                _lib.check(self.lib.cytof_global_fwd_f64(
+                    C.byref(g), _ptr(self.theta), _ptr(None), _ptr(self.stash), _ptr(self.globals),
+                    _ptr(self.zmask), _ptr(self.scalars_in), stream))
+            if self.peers is not None:
+                eng.fwdbwd_allreduce(batch, self.globals, self.zmask, self.packed, cg, self.peers)
+                self.peers.seq -= 1      # bookkeeping happens in graph_step
+            else:
+                eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, cg)
+                if m.dist_group is not None:
+                    torch.distributed.all_reduce(self.packed, group=m.dist_group)
+            with torch.cuda.device(self.dev):
+                _lib.check(self.lib.cytof_global_bwd_adam_f64(
+                    C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
+                    _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
+                    _ptr(self.step_dev), _ptr(self.flag), C.c_int32(1), stream))
+
+        self._graph_launches = 8 + (I if idx_buf is not None else 0)
+        self._graph_idx = idx_buf
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        return self
+
+    def graph_step(self):
+        """Replay the captured step; returns the device tensor [elbo, ll, lp, lq, scrubbed]."""
+        self.graph.replay()
+        self.t += 1
+        if self.peers is not None:
+            self.peers.seq += 1
+        self.launches += self._graph_launches
+        return self.scalars
+
+    def release_graph(self):
+        """back to host-driven steps (`step`)"""
+        self.graph = None
+        self.g.step_dev = None
+        self.eng.step_dev = None
+        if self.peers is not None:
+            self.peers.desc.seq_dev = None
 
     def step_from_host(self, y_pinned, update=True, no_missing=False):
         """The same full-batch step with the data matrix in PINNED HOST memory (`y_pinned`:

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CYTOF_ABI_VERSION 1
+#define CYTOF_ABI_VERSION 2
 #define CYTOF_MAX_SAMPLES 32 /* I */
 #define CYTOF_MAX_J 64       /* markers  */
 #define CYTOF_MAX_K 64       /* features */
@@ -71,6 +71,10 @@ typedef struct cytof_desc {
   int64_t row_base[CYTOF_MAX_SAMPLES];   /* first row of sample i inside y */
   int64_t row_global[CYTOF_MAX_SAMPLES]; /* global id of that row (rank offset; Philox counter) */
   double fac[CYTOF_MAX_SAMPLES];         /* N_i / B_i with GLOBAL counts, Model.py:257 */
+  /* CUDA-graph replay: if non-NULL (int64, device) the Philox counter word is *step_dev + 1,
+   * read on the device, and `step` is ignored.  cytof_global_bwd_adam_f64 bumps the counter at
+   * the end of a step, so one captured graph advances the noise / sampler / Adam step by itself. */
+  const int64_t* step_dev;
 } cytof_desc;
 
 /* `globals` (float, device): the transformed global sample of this step, packed as
@@ -126,6 +130,7 @@ typedef struct cytof_peer_desc {
   int32_t world, rank;
   uint64_t seq;
   void* mailbox[CYTOF_MAX_PEERS]; /* [rank] = own allocation, others = IPC mappings */
+  const int64_t* seq_dev;         /* non-NULL: seq = *seq_dev + 1, read on the device (CUDA graphs) */
 } cytof_peer_desc;
 size_t cytof_peer_mailbox_bytes(const cytof_desc* d, int32_t world);
 int cytof_peer_alloc(size_t bytes, void** ptr);
@@ -168,6 +173,9 @@ int cytof_adam_step_f64(double* param, const double* grad, double* exp_avg, doub
  * key = (seed, step, sample)), O(m) work and no scratch.  m >= N writes 0..N-1 (fit.py:98-99). */
 int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
                            int32_t* idx_out, void* stream);
+/* Same draw with the step read on the device (*step_dev + 1): capturable in a CUDA graph. */
+int cytof_sample_minibatch_dev(int64_t N, int64_t m, uint64_t seed, const int64_t* step_dev,
+                               int32_t sample, int32_t* idx_out, void* stream);
 
 /* ---- the O(3.5k-scalar) global part of a step as two single-CTA fp64 kernels ----------------
  * Replaces: model_param.py:46-92 (sample / transform / log|det J| / entropy of every global
@@ -192,6 +200,7 @@ typedef struct cytof_global_desc {
   double grad_scale; /* -1 / Nsum (fit.py:34) */
   double lr, beta1, beta2, adam_eps;
   int64_t adam_step; /* 1-based; ignored when step_dev != NULL */
+  const int64_t* step_dev; /* non-NULL: `step` (Philox counter of the global draw) = *step_dev + 1 */
 } cytof_global_desc;
 
 /* out[0] = R (global reals = noise length), out[1] = 2R (scrubbed prefix of theta),

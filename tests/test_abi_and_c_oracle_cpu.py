@@ -26,15 +26,17 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.cytof_abi_version() == 1
+    assert lib.cytof_abi_version() == 2
     assert lib.cytof_strerror(0) == b'ok' and b'shape' in lib.cytof_strerror(-2)
 
 
 def test_desc_struct_matches_header():
     hdr = open(os.path.join(ROOT, 'include', 'cytof_b200.h')).read()
     assert int(re.search(r'#define CYTOF_MAX_SAMPLES (\d+)', hdr).group(1)) == _lib.MAX_SAMPLES
-    # 8 int32 + 2 float + 2 uint64 + 33 int64 + 32 int64 + 32 int64 + 32 double
-    assert C.sizeof(_lib.Desc) == 8 * 4 + 2 * 4 + 2 * 8 + 33 * 8 + 3 * 32 * 8
+    # 8 int32 + 2 float + 2 uint64 + 33 int64 + 32 int64 + 32 int64 + 32 double + 1 pointer
+    assert C.sizeof(_lib.Desc) == 8 * 4 + 2 * 4 + 2 * 8 + 33 * 8 + 3 * 32 * 8 + 8
+    # cytof_peer_desc: 2 int32 + uint64 + 16 pointers + 1 pointer
+    assert C.sizeof(_lib.PeerDesc) == 2 * 4 + 8 + 16 * 8 + 8
     assert _lib.Desc.cell_begin.offset == 56
 
 

@@ -143,3 +143,51 @@ def test_posterior_label_sampler_matches_oracle():
     k_star = int(ref[0][:, 1:].mean(0).argmax()) + 1
     emp = (draws == k_star).mean()
     assert abs(emp - ref[0][:, k_star].mean()) < 0.03
+
+
+def _small_model(dev, nan_rate):
+    torch.manual_seed(0)
+    np.random.seed(0)
+    N, J, K, L = [600, 500, 700], 16, 8, [3, 3]
+    sim = cy.util.simdata_with_missing_values(N=N, J=J, a_W=[100.] * 5, L0=L[0], L1=L[1], seed=0, rate=nan_rate)
+    y = sim['data']['y']
+    pri = cy.model.default_priors(y, K=K, L=L, y_bounds=[-5., -3.5, -2.])
+    return cy.model.Model(y=[t.clone() for t in y], priors=pri, tau=0.1, verbose=-1, device=dev,
+                          noise='philox', seed=3)
+
+
+@pytest.mark.parametrize('mb,nan_rate', [(200, 0.2), (None, 0.0)])
+def test_cuda_graph_step_equals_host_driven_steps(mb, nan_rate):
+    """One captured CUDA graph (device sampler + global fwd + per-cell kernel + finalise + global bwd /
+    Adam, all step-dependent inputs read from a device counter) must reproduce, bit for bit, the
+    host-driven steps that pass the same step numbers through the descriptors."""
+    from cytofpy_b200.model.fused import FusedStep
+    from cytofpy_b200.model.train import device_minibatch
+    dev = torch.device('cuda', 0)
+    steps = 6
+    ref_mod = _small_model(dev, nan_rate)
+    ref = FusedStep(ref_mod, lr=0.05, seed=3)
+    hist_ref = []
+    for _ in range(steps):
+        s = ref.t + 1      # the step number the graph reads from its device counter
+        idx = [range(n) for n in ref_mod.N_local] if mb is None else device_minibatch(ref_mod, mb, s, ref.g.seed)
+        hist_ref.append(ref.step(idx).tolist())
+    g_mod = _small_model(dev, nan_rate)
+    gs = FusedStep(g_mod, lr=0.05, seed=3)
+    s = gs.t + 1
+    idx = [range(n) for n in g_mod.N_local] if mb is None else device_minibatch(g_mod, mb, s, gs.g.seed)
+    hist = [gs.step(idx).tolist()]             # step 1 host-driven, then capture
+    gs.capture(mb)
+    for _ in range(steps - 1):
+        hist.append(gs.graph_step().tolist())
+    assert gs.t == steps
+    assert np.array_equal(np.array(hist), np.array(hist_ref))
+    assert torch.equal(gs.theta, ref.theta)
+    gs.release_graph()
+    # and host-driven steps continue seamlessly after the graph is released
+    s = gs.t + 1
+    idx = [range(n) for n in g_mod.N_local] if mb is None else device_minibatch(g_mod, mb, s, gs.g.seed)
+    a = gs.step(idx).tolist()
+    s = ref.t + 1
+    idx = [range(n) for n in ref_mod.N_local] if mb is None else device_minibatch(ref_mod, mb, s, ref.g.seed)
+    assert a == ref.step(idx).tolist()
