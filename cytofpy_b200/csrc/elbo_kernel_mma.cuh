@@ -283,35 +283,32 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   auto prepass = [&](const int tn, const int b, unsigned& mmask, unsigned& amask) {
     float* src = sYb + b * (kTile * 32);
     mmask = 0u;
-    amask = 0u;
 #pragma unroll
     for (int u = 0; u < kTile; ++u) {
       const float yr = src[u * 32 + lane];
       mmask |= (yr != yr) ? (1u << u) : 0u;
     }
-    if (__any_sync(FULL, mmask != 0u)) {
-      unsigned long long grp_c = ~0ull;      // Philox block in the cache: 4 consecutive global rows
+    amask = __reduce_or_sync(FULL, mmask);       // cells of the tile with at least one missing marker
+    if (amask) {
+      unsigned long long grp_c = ~0ull;          // Philox block in the cache: 4 consecutive global rows
       float nz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1      // a real loop: ONE copy of the Philox rounds in the instruction stream
       for (int u = 0; u < kTile; ++u) {
-        const bool miss = (mmask >> u) & 1u;
-        if (__any_sync(FULL, miss)) {
-          amask |= 1u << u;
-          const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
-          float e = 0.f;
-          if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
-            if (miss && p.eps) e = __ldg(p.eps + (cb + c_lo + tn + u) * J + lane);
-          } else {
-            const unsigned long long grow = grow_base + (unsigned long long)row;
-            if ((grow >> 2) != grp_c) {      // warp-uniform
-              grp_c = grow >> 2;
-              philox_normal4(p.seed, elbo_step(p), grp_c, lane, nz);
-            }
-            const unsigned w = (unsigned)grow & 3u;
-            e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));
+        if (!((amask >> u) & 1u)) continue;      // warp-uniform
+        const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+        float e = 0.f;
+        if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
+          if (p.eps) e = __ldg(p.eps + (cb + c_lo + tn + u) * J + lane);
+        } else {
+          const unsigned long long grow = grow_base + (unsigned long long)row;
+          if ((grow >> 2) != grp_c) {            // warp-uniform
+            grp_c = grow >> 2;
+            philox_normal4(p.seed, elbo_step(p), grp_c, lane, nz);
           }
-          if (miss) src[u * 32 + lane] = e;
+          const unsigned w = (unsigned)grow & 3u;
+          e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));
         }
+        if ((mmask >> u) & 1u) src[u * 32 + lane] = e;
       }
     }
   };
