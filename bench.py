@@ -304,7 +304,7 @@ def run_ours(args, w, rank, world, local_rank):
             'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_mma_kernel (+finalize)', 'achieved': achieved,
                          'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read+write of one launch, ncu --set full (profiles/README.md)
-                         'traffic': 136.0e6 if args.workload == 'cfg4' else None,
+                         'traffic': 131.5e6 if args.workload == 'cfg4' else None,
                          'peak_source': peak_src, 'bytes_per_cell': bytes_cell, 'kernel_ms': k_ms,
                          'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
             'cpu_baseline': cpu,
