@@ -108,6 +108,7 @@ class FusedStep:
         self.launches = 0
         # multi-GPU: 'peer' (default) = one-shot all-reduce over peer memory fused into the finalise
         # kernel; 'nccl' = separate torch.distributed all-reduce (kept for A/B measurements)
+        self.graph = None
         self.peers = None
         if model.dist_group is not None and allreduce == 'peer':
             from .peer import PeerMailboxes

@@ -68,7 +68,7 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         y_mean_init=-3.0, y_sd_init=0.1, trace_every=None, eps_conv=1e-6, tau=0.1,
         backup_every=10, y_quantiles=[0, 35, 70], p_bounds=[.05, .8, .05], scale=1,
         use_stick_break=True, model_noisy=True, init_mp=None, verbose=1, flush=True,
-        K=30, L=None, device=None, sampler='device', noise='philox', fused=True):
+        K=30, L=None, device=None, sampler='device', noise='philox', fused=True, graph=True):
     """reference fit.py:50-147, same arguments and the same returned dict keys
     ('elbo', 'trace', 'mp', 'tau', 'vae', 'use_stick_break', 'y', 'priors', 'model_noisy').
 
@@ -77,7 +77,8 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
     'numpy' = the reference's np.random.choice stream), noise ('philox' | 'external'), fused
     (True: the whole step runs as 4-5 kernel launches, cytofpy_b200/model/fused.py, when the
     priors are of the default families; False / other priors: torch autograd + torch Adam
-    around the fused per-cell kernel)."""
+    around the fused per-cell kernel), graph (True: with the fused path and the device sampler,
+    every step after the first is ONE CUDA-graph replay, FusedStep.capture)."""
     print('scale: {}'.format(scale))
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -107,13 +108,22 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
     best_vae = copy.deepcopy(model.y_vae)
     elbo_hist, trace = [], []
     for t in range(max_iter + 1):
-        if sampler == 'numpy':
+        replay = stepper is not None and graph and sampler == 'device' and t >= 1
+        if replay:
+            idx = None      # the captured graph draws its own minibatch on the device
+        elif sampler == 'numpy':
             idx = [np.arange(n) if minibatch_size >= n else
                    np.random.choice(n, minibatch_size, replace=False) for n in model.N_local]
         else:
             idx = device_minibatch(model, minibatch_size, t, seed)
         if stepper is not None:
-            elbo_t, ll, lp, lq, scrubbed = stepper.step(idx).tolist()     # one 40-byte read-back
+            if replay:
+                if stepper.graph is None:
+                    stepper.capture(minibatch_size)
+                out_t = stepper.graph_step()
+            else:
+                out_t = stepper.step(idx)
+            elbo_t, ll, lp, lq, scrubbed = out_t.tolist()     # one 40-byte read-back
             fixed_grad = scrubbed != 0.0
             if fixed_grad:
                 print("WARNING: Setting a nan gradient to zero!")
