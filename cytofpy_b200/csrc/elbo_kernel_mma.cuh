@@ -358,9 +358,8 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   auto phase_a2 = [&](const int u, const AState& st) {
     const float A0 = st.B0 + fast_lg2(st.S0), A1 = st.B1 + fast_lg2(st.S1);
     const float rr = fast_rcp(st.S0 * st.S1);      // one reciprocal for both mixtures (S in [1, L])
-    sR0[u * 32 + lane] = rr * st.S1;
-    sR1[u * 32 + lane] = rr * st.S0;
-    sD[u * kTS + lane] = okf * (A1 - A0);
+    reinterpret_cast<float2*>(sR0)[u * 32 + lane] = make_float2(rr * st.S1, rr * st.S0);   // 1/S0, 1/S1
+    sD[u * kTS + lane] = A1 - A0;           // markers >= J: Z has zero rows there, the value is never used
     sA[u * kTS + lane] = okf * A0;
     if (NOISY) sY[u * kTS + lane] = st.yy;
   };
@@ -368,13 +367,14 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   // mixtures of cell u, backward: w_zl = c_z p_zl; statistics sum w and sum w y' per component,
   // sum c_z y_z'^2 per cell (sum_l w_zl = c_z) -- three FMA-pipe ops per component pair
   auto phase_b = [&](const int u, const float* src, const unsigned mmask, const unsigned amask) {
-    const float c1 = okf * sA[u * kTS + lane];
+    const float c1 = sA[u * kTS + lane];    // = 0 for markers >= J (zero rows of Z)
     const float c0 = okf * sS[u] - c1;
     const float x = src[u * 32 + lane];
     const float yv = (MISSING && ((mmask >> u) & 1u)) ? fmaf(sd, x, vm) : x;
     const float y0 = yv - mc0, y1 = yv - mc1;
     const float2 Y00 = bcp(y0), Y11 = bcp(y1), Y01 = mkp(y0, y1);
-    const float r0 = c0 * sR0[u * 32 + lane], r1 = c1 * sR1[u * 32 + lane];
+    const float2 rs01 = reinterpret_cast<const float2*>(sR0)[u * 32 + lane];
+    const float r0 = c0 * rs01.x, r1 = c1 * rs01.y;
     const float2 R00 = bcp(r0), R11 = bcp(r1), R01 = mkp(r0, r1);
     sq = fmaf(c0 * y0, y0, fmaf(c1 * y1, y1, sq));
     float2 wm = bcp(0.f);
