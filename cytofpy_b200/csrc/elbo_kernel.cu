@@ -23,6 +23,7 @@
 #include "elbo_kernel_j32.cuh"
 #include "elbo_kernel_mma.cuh"
 #include "elbo_kernel_mma4.cuh"
+#include "elbo_kernel_mma64.cuh"
 
 namespace cytof {
 
@@ -687,6 +688,25 @@ static const Variant kVariants[] = {
     CYTOF_VARIANT(3, 3, 2, 2), CYTOF_VARIANT(5, 5, 2, 2), CYTOF_VARIANT(8, 8, 2, 2),
 };
 
+// 32 < J <= 48, K <= 64, data without missing entries (cfg5): tensor-core kernel with CTA-cooperative
+// dZ (elbo_kernel_mma64.cuh).  fn index = noisy + 2 * has_idx + 4 * (tail passes - 1).
+#define CYTOF_VARIANT_MMA64(a, b) \
+  { a, b, 2, 2, kXWarpFloats, kXZFloats, { elbo_fwdbwd_mma64_kernel<a, b, false, false, 1>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 1>, \
+                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 1>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 1>, \
+                             elbo_fwdbwd_mma64_kernel<a, b, false, false, 2>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 2>, \
+                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 2>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 2> }, true, kXThreads }
+#ifndef CYTOF_MMA64
+#define CYTOF_MMA64 1
+#endif
+static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5), CYTOF_VARIANT_MMA64(8, 8) };
+static const Variant* pick_variant64(const cytof_desc* d) {
+  if (!CYTOF_MMA64 || !(d->flags & CYTOF_FLAG_NO_MISSING)) return nullptr;
+  if (d->J <= 32 || d->J > 48 || d->K > 64) return nullptr;
+  for (const Variant& v : kVariants64)
+    if (v.lm0 >= d->L0 && v.lm1 >= d->L1) return &v;
+  return nullptr;
+}
+
 static const Variant* pick_variant(int J, int K, int L0, int L1) {
   const int jp = J <= 32 ? 1 : 2, kp = K <= 32 ? 1 : 2;
   const int need = jp > kp ? jp : kp;
@@ -725,11 +745,12 @@ int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAM
 // resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached per
 // device; re-evaluated when a different problem shape changes the shared-memory footprint)
 struct OccEntry { size_t smem, smem_attr; int occ; };
-static OccEntry g_occ[64][16][8] = {};
+static OccEntry g_occ[64][20][8] = {};
 static int variant_occupancy(const Variant* v, int fi, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
-  OccEntry& e = g_occ[dev][(int)(v - kVariants)][fi];
+  const bool is64 = v >= kVariants64 && v < kVariants64 + 2;
+  OccEntry& e = g_occ[dev][is64 ? 16 + (int)(v - kVariants64) : (int)(v - kVariants)][fi];
   if (e.occ == 0 || e.smem != smem) {
     if (smem > 48 * 1024 && smem > e.smem_attr) {   // opt in to large dynamic shared memory
       cudaFuncSetAttribute(v->fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -825,7 +846,8 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
                   double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
                   cudaError_t* err, const cytof_peer_desc* peer) {
-  const Variant* v = pick_variant(d->J, d->K, d->L0, d->L1);
+  const Variant* v64 = pick_variant64(d);
+  const Variant* v = v64 ? v64 : pick_variant(d->J, d->K, d->L0, d->L1);
   ElboParams p;
   fill_params(d, &p);
   p.y = y; p.idx = idx; p.eps = eps; p.globals = globals;
@@ -834,7 +856,8 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15;
   p.partials = reinterpret_cast<float*>(wp);
   const size_t smem = fused_smem_bytes(v, d->J, d->K, d->L0, d->L1);
-  const int fi = (d->model_noisy ? 1 : 0) + (idx ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
+  const int fi = v64 ? (d->model_noisy ? 1 : 0) + (idx ? 2 : 0) + (d->J - 32 > 8 ? 4 : 0)
+                     : (d->model_noisy ? 1 : 0) + (idx ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
   const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem));
   const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
   const size_t need = sizeof(float) * (size_t)pl.total * (size_t)nblocks + (wp - reinterpret_cast<uintptr_t>(workspace));

@@ -1,0 +1,585 @@
+// Tensor-core fused ELBO kernel for 32 < J <= 48 markers, K <= 64 features, L <= 8 components and
+// data without missing entries (BASELINE cfg5: J = 40, K = 50, L = 8/8).
+//
+// The first SIMT kernel needs 1,767 warp-instructions per cell at these shapes (bit-mask Z gating,
+// two markers per lane, register spills; profiles/README.md).  This kernel keeps the structure of
+// elbo_kernel_mma4.cuh (4 cells per warp tile, hi/lo halves of the TF32 split as MMA columns,
+// expanded-quadratic forward, moment-based backward) and adds what the larger shapes need:
+//   * markers 0..31 run with lane = marker, one warp pass per cell; the J - 32 TAIL markers of
+//     several cells are packed into ONE warp pass (lane = (cell, tail marker): 4 cells x 8 markers or
+//     2 cells x 16), so the 19 MUFU per (cell, marker) are issued with 100 % / 83 % of the lanes live
+//     instead of 62 % with "two markers per lane";
+//   * Z^T . D^T is 4 m-tiles x ceil(J/8) k-chunks, Z . e^T is 3 m-tiles x ceil(K/8) k-chunks;
+//   * dZ (48 x 64) would be 96 accumulator registers per thread if every warp kept its own copy.
+//     Instead the CTA works in ROUNDS of 8 tiles: after the contraction stage of a round every
+//     warp's D and g tiles are in shared memory, one __syncthreads, and warp w accumulates the
+//     n-tile w of dZ (features 8w..8w+7, all markers: 12 registers) over the tiles of ALL warps.
+//     The tiles are double-buffered, so one barrier per round suffices.
+#pragma once
+#include "elbo_kernel_mma4.cuh"
+
+namespace cytof {
+
+constexpr int kXThreads = 256;
+constexpr int kXWarps = kXThreads / 32;
+constexpr int kXT = 4;                    // cells per warp tile
+constexpr int kXDS = 52;                  // row stride of the D / A0 / y^2 tiles (48 markers, conflict-free ldmatrix)
+constexpr int kXGS = 68;                  // row stride of the e / g tile (64 features)
+constexpr int kXJS = 48;                  // row stride of the y buffer
+constexpr int kXMTK = 4, kXMTJ = 3;       // m-tiles over features (64) and over markers (48)
+constexpr int kXNCJ = 6, kXNCK = 8;       // k-chunks of 8 over markers and over features
+constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4;
+// per warp (floats): D hi/lo [2][8][52] | g hi/lo [2][8][68] | A0/c1 [4][52] | y^2 [4][52] |
+// 1/S0,1/S1 [6 units][32] float2 | per-cell scalars [16] | y double buffer [2][4][48]
+constexpr int kXWarpFloats = 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS + 6 * 32 * 2 + 16 + 2 * kXT * kXJS;
+
+template <int LM0, int NC, int NPT>
+__device__ __forceinline__ void mix_forward(const float yv, const float mc0, const float mc1, const float nh2,
+                                            const float2 (&be)[NPT], const float2 (&al)[NPT], float2 (&ee)[NPT],
+                                            float& S0, float& S1, float& B0, float& B1) {
+  const float y0 = yv - mc0, y1 = yv - mc1;
+  const float2 Y00 = bcp(y0), Y11 = bcp(y1), Y01 = mkp(y0, y1);
+  float2 v[NPT];
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) {
+    const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
+    v[q] = fma2(be[q], lo1 ? Y11 : (hi1 ? Y01 : Y00), al[q]);
+  }
+  float M0 = kNegBig, M1 = kNegBig;
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
+  const float2 M00 = bcp(M0), M11 = bcp(M1), M01 = mkp(M0, M1);
+  float2 s0 = bcp(0.f), s1 = bcp(0.f);
+  float s0x = 0.f, s1x = 0.f;
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) {
+    const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0, hi_live = 2 * q + 1 < NC;
+    const float2 tt = sub2(v[q], lo1 ? M11 : (hi1 ? M01 : M00));
+    ee[q] = mkp(fast_ex2(lo2(tt)), hi_live ? fast_ex2(hi2(tt)) : 0.f);
+    if (lo1) s1 = add2(s1, ee[q]);
+    else if (!hi1) s0 = add2(s0, ee[q]);
+    else { s0x = lo2(ee[q]); s1x = hi2(ee[q]); }
+  }
+  S0 = (lo2(s0) + hi2(s0)) + s0x;
+  S1 = (lo2(s1) + hi2(s1)) + s1x;
+  B0 = fmaf(nh2 * y0, y0, M0);      // A_z = B_z + lg2(S_z)
+  B1 = fmaf(nh2 * y1, y1, M1);
+}
+
+template <int LM0, int NPT>
+__device__ __forceinline__ void mix_backward(const float yv, const float mc0, const float mc1, const float c0,
+                                             const float c1, const float2 rs01, const float2 (&ee)[NPT],
+                                             float2 (&sw)[NPT], float2 (&swy)[NPT], float& sq) {
+  const float y0 = yv - mc0, y1 = yv - mc1;
+  const float2 Y00 = bcp(y0), Y11 = bcp(y1), Y01 = mkp(y0, y1);
+  const float r0 = c0 * rs01.x, r1 = c1 * rs01.y;
+  const float2 R00 = bcp(r0), R11 = bcp(r1), R01 = mkp(r0, r1);
+  sq = fmaf(c0 * y0, y0, fmaf(c1 * y1, y1, sq));
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) {
+    const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
+    const float2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[q]);
+    acc_add2(sw[q], w);
+    acc_fma2(swy[q], w, lo1 ? Y11 : (hi1 ? Y01 : Y00));
+  }
+}
+
+// NTP = tail passes per 4-cell tile: 1 (J - 32 <= 8: 4 cells x 8 tail markers per pass) or
+//                                    2 (J - 32 <= 16: 2 cells x 16 tail markers per pass)
+template <int LM0, int LM1, bool NOISY, bool HAS_IDX, int NTP>
+__global__ void __launch_bounds__(kXThreads, 1)
+elbo_fwdbwd_mma64_kernel(const ElboParams p) {
+  constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;
+  constexpr int CPT = kXT / NTP, TP = 32 / CPT;            // cells and (padded) tail markers per tail pass
+  constexpr int NU = kXT + NTP;                             // mixture units (warp passes) per tile
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  uint4* sZT = reinterpret_cast<uint4*>(smem);              // [mt < 4][c < 6][lane]  A fragments of Z^T (k x j)
+  uint4* sZ = sZT + kXMTK * kXNCJ * 32;                     // [mt < 3][c < 8][lane]  A fragments of Z   (j x k)
+  float* wbase0 = smem + kXZFloats;
+  float* wbase = wbase0 + warp * kXWarpFloats;
+  float* sDb = wbase;                              // [2][8][kXDS] row 2c = hi(D) of cell c, 2c+1 = lo(D)
+  float* sGb = sDb + 2 * 8 * kXDS;                 // [2][8][kXGS] e, then g = fac rho softmax: hi / lo rows
+  float* sA = sGb + 2 * 8 * kXGS;                  // [4][kXDS] A0_j, later c1_j
+  float* sY = sA + kXT * kXDS;                     // [4][kXDS] y_j^2
+  float2* sR = reinterpret_cast<float2*>(sY + kXT * kXDS);   // [NU][32] (1/S0, 1/S1) per unit and lane
+  float* sS = reinterpret_cast<float*>(sR + 6 * 32);          // [0..3] fac rho, [4..7] fac (1-rho), [8..11] sc
+  float* sYb = sS + 16;                            // [2][4][kXJS] y rows
+  float* sred = smem;
+
+  const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
+  int i = 0;
+  while (i + 1 < I && (int)blockIdx.x >= p.blk_begin[i + 1]) ++i;
+  const int nb = p.blk_begin[i + 1] - p.blk_begin[i];
+  const int lb = (int)blockIdx.x - p.blk_begin[i];
+  const long long cb = p.cell_begin[i];
+  const long long Bi = p.cell_begin[i + 1] - cb;
+  const long long c_lo = Bi * lb / nb, c_hi = Bi * (lb + 1) / nb;
+  const long long row_base = p.row_base[i];
+  const int ncj = (J + 7) >> 3, nck = (K + 7) >> 3, mtk = (K + 15) >> 4, mtj = (J + 15) >> 4;
+
+  // ---------------- Z fragment tables, zeroed tiles ----------------
+  for (int e = threadIdx.x; e < (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32; e += kXThreads) {
+    const bool second = e >= kXMTK * kXNCJ * 32;
+    const int e2 = second ? e - kXMTK * kXNCJ * 32 : e;
+    const int ln = e2 & 31, mc = e2 >> 5;
+    const int mt = second ? mc / kXNCK : mc / kXNCJ, c = second ? mc % kXNCK : mc % kXNCJ;
+    const int gg = ln >> 2, tt = ln & 3;
+    uint32_t v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = 16 * mt + gg + ((r & 1) ? 8 : 0), col = 8 * c + tt + ((r & 2) ? 4 : 0);
+      const int j = second ? row : col, k = second ? col : row;   // first: Z^T[k][j], second: Z[j][k]
+      const unsigned long long zr = (j < J && k < K) ? p.zmask[j] : 0ull;
+      v[r] = ((zr >> k) & 1ull) ? 0x3f800000u : 0u;
+    }
+    (second ? sZ : sZT)[mc * 32 + ln] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  for (int e = lane; e < 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS; e += 32) wbase[e] = 0.f;   // D, g, A0, y^2 tiles
+
+  // ---------------- per-sample constants ----------------
+  const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
+  const float* __restrict__ G = p.globals;
+  const float sig = G[gl.sig + i];
+  const float inv_sig2 = 1.0f / (sig * sig);
+  const float nh2 = -0.5f * inv_sig2 * kLog2e;
+  const float cbase = (-logf(sig) - kHalfLog2Pi) * kLog2e;
+  const float fac = p.fac[i];
+  // tail lane -> (cell within the pass, tail marker)
+  const int tcell = lane / TP, jt = 32 + lane % TP;
+  const bool tail_ok = jt < J;
+  const float tokf = tail_ok ? 1.f : 0.f;
+
+  float2 mup[NPT], be[NPT], alm[NPT], alt[NPT];      // alm: marker `lane`, alt: tail marker jt
+  float mc0, mc1;
+  {
+    const float m0a = G[gl.mu0], m0b = G[gl.mu0 + L0 - 1], m1a = G[gl.mu1], m1b = G[gl.mu1 + L1 - 1];
+    mc0 = 0.5f * (m0a + m0b);
+    mc1 = 0.5f * (m1a + m1b);
+    float m[2 * NPT], b[2 * NPT], am[2 * NPT], at[2 * NPT];
+    const int jtt = tail_ok ? jt : 0;
+#pragma unroll
+    for (int x = 0; x < 2 * NPT; ++x) {
+      const bool z1 = x >= LM0;
+      const int l = z1 ? x - LM0 : x, Lz = z1 ? L1 : L0;
+      const bool live = l < Lz && x < LM0 + LM1;
+      const int ll = live ? l : 0;
+      m[x] = live ? G[(z1 ? gl.mu1 : gl.mu0) + ll] - (z1 ? mc1 : mc0) : 0.f;
+      b[x] = live ? -2.f * nh2 * m[x] : 0.f;
+      const float base = fmaf(nh2 * m[x], m[x], cbase);
+      const float* le = G + (z1 ? gl.le1 : gl.le0);
+      am[x] = live ? fmaf(le[(i * J + lane) * Lz + ll], kLog2e, base) : kNegBig;
+      at[x] = (tail_ok && live) ? fmaf(le[(i * J + jtt) * Lz + ll], kLog2e, base) : (l == 0 ? 0.f : kNegBig);
+    }
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      mup[q] = mkp(m[2 * q], m[2 * q + 1]);
+      be[q] = mkp(b[2 * q], b[2 * q + 1]);
+      alm[q] = mkp(am[2 * q], am[2 * q + 1]);
+      alt[q] = mkp(at[2 * q], at[2 * q + 1]);
+    }
+  }
+  // log W (log2 domain) of the 8 feature rows of this thread in the accumulator layout: 16 mt + g (+8)
+  float lwk[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = 16 * (r >> 1) + g + 8 * (r & 1);
+    lwk[r] = k < K ? G[gl.lw + i * K + k] * kLog2e : kNegBig;
+  }
+  float l1me2 = 0.f, zconst2 = 0.f, ninv2s2 = 0.f;
+  if (NOISY) {
+    const float e_i = G[gl.eps + i];
+    l1me2 = log1pf(-e_i) * kLog2e;
+    zconst2 = ((float)J * (-kHalfLog2Pi - logf(p.noisy_sd)) + logf(e_i)) * kLog2e;
+    ninv2s2 = -0.5f / (p.noisy_sd * p.noisy_sd) * kLog2e;
+  }
+
+  // ---------------- accumulators ----------------
+  float2 swm[NPT], swym[NPT], swt[NPT], swyt[NPT];
+  float sq = 0.f;                        // sum c_z y_z'^2 over all of this lane's units
+  float dZ[kXMTJ][4];                    // n-tile `warp` of dZ, all 3 m-tiles (markers permuted, see epilogue)
+  float gW[8];
+  float sfr = 0.f, sfo = 0.f;
+  double ll2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) swm[q] = swym[q] = swt[q] = swyt[q] = bcp(0.f);
+#pragma unroll
+  for (int a = 0; a < kXMTJ; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dZ[a][c] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) gW[r] = 0.f;
+
+  // ---------------- rounds ----------------
+  const int32_t* __restrict__ idx = p.idx + (HAS_IDX ? (cb + c_lo) : 0);
+  const float* __restrict__ ysamp = p.y + (size_t)row_base * J;
+  const int ncell = (int)(c_hi - c_lo);
+  const int first_row = (int)c_lo;
+  const int nrounds = (ncell + kXWarps * kXT - 1) / (kXWarps * kXT);      // CTA-uniform
+  const bool vec16 = !HAS_IDX && (J & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;
+
+  // y rows of this warp's tile of round r -> sYb[b] (row stride kXJS); rows past the range are zeros
+  auto issue_tile = [&](const int r, const int b) {
+    const int tn = (r * kXWarps + warp) * kXT;
+    float* dst = sYb + b * (kXT * kXJS);
+#pragma unroll
+    for (int u = 0; u < kXT; ++u) {
+      if (tn + u < ncell) {
+        const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+        const float* src = ysamp + (size_t)row * J;
+        if (vec16) {
+          if (4 * lane < J) cp_async16(dst + u * kXJS + 4 * lane, src + 4 * lane);
+        } else {
+          cp_async4(dst + u * kXJS + lane, src + lane);
+          if (32 + lane < J) cp_async4(dst + u * kXJS + 32 + lane, src + 32 + lane);
+        }
+      } else {
+        dst[u * kXJS + lane] = 0.f;
+        if (lane < kXJS - 32) dst[u * kXJS + 32 + lane] = 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  float2 ee[NU][NPT];
+
+  // forward of unit `un` of the tile whose y rows are in `src`; writes the tiles of buffer `b`
+  auto phase_a = [&](const int un, const float* src, const int b) {
+    float* sD = sDb + b * (8 * kXDS);
+    float S0, S1, B0, B1;
+    if (un < kXT) {                               // main pass: cell un, marker lane
+      const float yv = src[un * kXJS + lane];
+      mix_forward<LM0, NC, NPT>(yv, mc0, mc1, nh2, be, alm, ee[un], S0, S1, B0, B1);
+      const float A0 = B0 + fast_lg2(S0), A1 = B1 + fast_lg2(S1);
+      const float rr = fast_rcp(S0 * S1);
+      sR[un * 32 + lane] = make_float2(rr * S1, rr * S0);
+      uint32_t dh, dl;
+      split_tf32(A1 - A0, dh, dl);
+      sD[(2 * un) * kXDS + lane] = __uint_as_float(dh);
+      sD[(2 * un + 1) * kXDS + lane] = __uint_as_float(dl);
+      sA[un * kXDS + lane] = A0;
+      if (NOISY) sY[un * kXDS + lane] = yv * yv;
+    } else {                                      // tail pass: cell cu, tail marker jt
+      const int cu = (un - kXT) * CPT + tcell;
+      const float yv = tail_ok ? src[cu * kXJS + jt] : 0.f;
+      mix_forward<LM0, NC, NPT>(yv, mc0, mc1, nh2, be, alt, ee[un], S0, S1, B0, B1);
+      const float A0 = B0 + fast_lg2(S0), A1 = B1 + fast_lg2(S1);
+      const float rr = fast_rcp(S0 * S1);
+      sR[un * 32 + lane] = make_float2(rr * S1, rr * S0);
+      uint32_t dh, dl;
+      split_tf32(tokf * (A1 - A0), dh, dl);
+      if (jt < kXJS) {
+        sD[(2 * cu) * kXDS + jt] = __uint_as_float(dh);
+        sD[(2 * cu + 1) * kXDS + jt] = __uint_as_float(dl);
+        sA[cu * kXDS + jt] = tokf * A0;
+        if (NOISY) sY[cu * kXDS + jt] = yv * yv;
+      }
+    }
+  };
+  auto phase_b = [&](const int un, const float* src) {
+    if (un < kXT) {
+      const float c1 = sA[un * kXDS + lane];
+      const float c0 = sS[un] - c1;
+      mix_backward<LM0, NPT>(src[un * kXJS + lane], mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], swm, swym, sq);
+    } else {
+      const int cu = (un - kXT) * CPT + tcell;
+      const float c1 = tail_ok ? sA[cu * kXDS + jt] : 0.f;
+      const float c0 = tokf * sS[cu] - c1;
+      const float yv = tail_ok ? src[cu * kXJS + jt] : 0.f;
+      mix_backward<LM0, NPT>(yv, mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], swt, swyt, sq);
+    }
+  };
+
+  if (nrounds > 0) {
+    issue_tile(0, 0);
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int un = 0; un < NU; ++un) phase_a(un, sYb, 0);
+    if (nrounds > 1) issue_tile(1, 1);
+  }
+  __syncthreads();   // Z tables visible
+
+  for (int r = 0; r < nrounds; ++r) {
+    const int b = r & 1;
+    const int t0 = (r * kXWarps + warp) * kXT;
+    const bool valid = t0 + t4 < ncell;        // this thread's cell (t4) in the accumulator layout
+    float* sD = sDb + b * (8 * kXDS);
+    float* sG = sGb + b * (8 * kXGS);
+    __syncwarp();
+
+    // ===== contraction 1: f^T[k, (n, hi|lo)] = Z^T . [D_hi | D_lo]^T (+ log W on the hi column)
+    float fT[kXMTK][4];
+    {
+      uint32_t rb[12];     // B fragments: block q = markers 4q..4q+3, column g = row g of the D tile
+#pragma unroll
+      for (int q4 = 0; q4 < 3; ++q4) {
+        uint32_t r4[4];
+        ldsm_x4(sD + (lane & 7) * kXDS + 16 * q4 + 4 * (lane >> 3), r4);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) rb[4 * q4 + m] = r4[m];
+      }
+#pragma unroll
+      for (int mt = 0; mt < kXMTK; ++mt) {
+        fT[mt][0] = lwk[2 * mt];
+        fT[mt][2] = lwk[2 * mt + 1];
+        fT[mt][1] = fT[mt][3] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < kXNCJ; ++c) {
+        if (c < ncj) {
+#pragma unroll
+          for (int mt = 0; mt < kXMTK; ++mt)
+            if (mt < mtk) mma_tf32(fT[mt], sZT[(mt * kXNCJ + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
+        }
+      }
+    }
+    float f[8];
+#pragma unroll
+    for (int mt = 0; mt < kXMTK; ++mt) {
+      f[2 * mt] = fT[mt][0] + fT[mt][1];        // feature 16 mt + g
+      f[2 * mt + 1] = fT[mt][2] + fT[mt][3];    // feature 16 mt + g + 8
+    }
+    float mx = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    float ex[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ex[q] = fast_ex2(f[q] - mx);
+      uint32_t eh, el;
+      split_tf32(ex[q], eh, el);
+      const int k = 16 * (q >> 1) + g + 8 * (q & 1);
+      sG[(2 * t4) * kXGS + k] = __uint_as_float(eh);
+      sG[(2 * t4 + 1) * kXGS + k] = __uint_as_float(el);
+    }
+    __syncwarp();
+
+    // ===== contraction 2 on the numerators: c1'^T[j, (n, hi|lo)] = Z . [e_hi | e_lo]^T
+    float cT[kXMTJ][4];
+    {
+      uint32_t rb[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t r4[4];
+        ldsm_x4(sG + (lane & 7) * kXGS + 16 * q4 + 4 * (lane >> 3), r4);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) rb[4 * q4 + m] = r4[m];
+      }
+#pragma unroll
+      for (int mt = 0; mt < kXMTJ; ++mt) cT[mt][0] = cT[mt][1] = cT[mt][2] = cT[mt][3] = 0.f;
+#pragma unroll
+      for (int c = 0; c < kXNCK; ++c) {
+        if (c < nck) {
+#pragma unroll
+          for (int mt = 0; mt < kXMTJ; ++mt)
+            if (mt < mtj) mma_tf32(cT[mt], sZ[(mt * kXNCK + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
+        }
+      }
+    }
+    // ===== per-cell scalars (cell t4): logsumexp over K, noisy class
+    float rs = ((ex[0] + ex[1]) + (ex[2] + ex[3])) + ((ex[4] + ex[5]) + (ex[6] + ex[7]));
+    float ra, ry = 0.f;
+    {
+      const float4 a4 = *reinterpret_cast<const float4*>(sA + t4 * kXDS + 4 * g);
+      const float2 a2 = *reinterpret_cast<const float2*>(sA + t4 * kXDS + 32 + 2 * g);
+      ra = ((a4.x + a4.y) + (a4.z + a4.w)) + (a2.x + a2.y);
+      if (NOISY) {
+        const float4 c4 = *reinterpret_cast<const float4*>(sY + t4 * kXDS + 4 * g);
+        const float2 c2 = *reinterpret_cast<const float2*>(sY + t4 * kXDS + 32 + 2 * g);
+        ry = ((c4.x + c4.y) + (c4.z + c4.w)) + (c2.x + c2.y);
+      }
+    }
+    {
+      float2 rr = mkp(rs, ra);
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        rr = add2(rr, shfl_xor2(rr, o));
+        if (NOISY) ry += __shfl_xor_sync(FULL, ry, o);
+      }
+      rs = lo2(rr);
+      ra = hi2(rr);
+    }
+    const float facc = valid ? fac : 0.f;
+    const float lse2 = (mx + ra) + fast_lg2(rs);
+    const float rinv = fast_rcp(rs);
+    float rho = 1.f, omr = 0.f, L2 = lse2;
+    if (NOISY) {
+      const float q2 = lse2 + l1me2;
+      const float z2 = fmaf(ninv2s2, ry, zconst2);
+      const float dd = q2 - z2;
+      const float tq = fast_ex2(-fabsf(dd));
+      const float r1 = fast_rcp(1.f + tq);
+      L2 = fmaxf(q2, z2) + fast_lg2(1.f + tq);
+      rho = dd >= 0.f ? r1 : tq * r1;
+      omr = dd >= 0.f ? tq * r1 : r1;
+    }
+    if (valid) ll2 += (double)L2;
+    const float fr = facc * rho;
+    const float sc = fr * rinv;               // g_k = sc e_k
+    sfr += fr;
+    sfo = fmaf(facc, omr, sfo);
+    if (g == 0) {
+      sS[t4] = fr;
+      sS[4 + t4] = facc * omr;
+    }
+    __syncwarp();      // every lane has its e fragments (ldmatrix) and its A0 sums: the tiles may be rewritten
+    // c1 = sc * (hi + lo columns) over the A0 tile; g = sc e, split, over the e tile (for dZ)
+#pragma unroll
+    for (int mt = 0; mt < kXMTJ; ++mt) {
+      const int j0 = 16 * mt + g;
+      if (j0 < kXJS) sA[t4 * kXDS + j0] = sc * (cT[mt][0] + cT[mt][1]);
+      if (j0 + 8 < kXJS) sA[t4 * kXDS + j0 + 8] = sc * (cT[mt][2] + cT[mt][3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float gv = sc * ex[q];
+      gW[q] += gv;
+      uint32_t gh, gl2;
+      split_tf32(gv, gh, gl2);
+      const int k = 16 * (q >> 1) + g + 8 * (q & 1);
+      sG[(2 * t4) * kXGS + k] = __uint_as_float(gh);
+      sG[(2 * t4 + 1) * kXGS + k] = __uint_as_float(gl2);
+    }
+    __syncthreads();   // the D and g tiles of ALL warps for this round are complete
+
+    // ===== contraction 3 (CTA-cooperative): this warp owns features 8 warp .. 8 warp + 7 of dZ and
+    // walks the tiles of all 8 warps; contraction index = (cell, hi|lo of D); markers permuted so that
+    // the 6 values a thread needs are contiguous: rows g / g+8 of m-tile mt = markers 6g+2mt / 6g+2mt+1
+    if (8 * warp < K) {
+#pragma unroll 2
+      for (int s = 0; s < kXWarps; ++s) {
+        const float* tD = wbase0 + s * kXWarpFloats + b * (8 * kXDS);
+        const float* tG = wbase0 + s * kXWarpFloats + 2 * 8 * kXDS + b * (8 * kXGS);
+        const uint32_t gh = __float_as_uint(tG[(2 * t4) * kXGS + 8 * warp + g]);
+        const uint32_t gl2 = __float_as_uint(tG[(2 * t4 + 1) * kXGS + 8 * warp + g]);
+#pragma unroll
+        for (int mt = 0; mt < kXMTJ; ++mt) {
+          const float2 dh = *reinterpret_cast<const float2*>(tD + (2 * t4) * kXDS + 6 * g + 2 * mt);
+          const float2 dl = *reinterpret_cast<const float2*>(tD + (2 * t4 + 1) * kXDS + 6 * g + 2 * mt);
+          const uint4 a = make_uint4(__float_as_uint(dh.x), __float_as_uint(dh.y), __float_as_uint(dl.x), __float_as_uint(dl.y));
+          mma_tf32(dZ[mt], a, gh, gh);                                   // D_hi g_hi + D_lo g_hi
+          mma_tf32(dZ[mt], make_uint4(a.x, a.y, 0u, 0u), gl2, 0u);       // D_hi g_lo
+        }
+      }
+    }
+
+    // ===== backward of this round's tile, interleaved unit by unit with the forward of the next
+    const float* ycur = sYb + b * (kXT * kXJS);
+    if (r + 1 < nrounds) {
+      const float* ynxt = sYb + (b ^ 1) * (kXT * kXJS);
+      cp_async_wait<0>();
+      __syncwarp();
+#pragma unroll
+      for (int un = 0; un < NU; ++un) {
+        phase_b(un, ycur);
+        phase_a(un, ynxt, b ^ 1);
+      }
+    } else {
+#pragma unroll
+      for (int un = 0; un < NU; ++un) phase_b(un, ycur);
+    }
+    __syncwarp();
+    if (r + 2 < nrounds) issue_tile(r + 2, b);
+  }
+
+  // ---------------- CTA reduction (fixed order) and partial record ----------------
+  const PartialLayout pl = partial_layout(J, K, L0, L1);
+  // sum w d = sum w y' - mu' sum w;  sum w d^2 = sum c y'^2 - sum_l mu'_l (2 sum w y' - mu'_l sum w)
+  float swdf[2 * NPT];
+  float swdd_l = sq;
+#pragma unroll
+  for (int x = 0; x < 2 * NPT; ++x) {
+    const float m = (x & 1) ? hi2(mup[x / 2]) : lo2(mup[x / 2]);
+    const float a = ((x & 1) ? hi2(swm[x / 2]) : lo2(swm[x / 2]));
+    const float bm = ((x & 1) ? hi2(swym[x / 2]) : lo2(swym[x / 2]));
+    const float at = ((x & 1) ? hi2(swt[x / 2]) : lo2(swt[x / 2]));
+    const float bt = ((x & 1) ? hi2(swyt[x / 2]) : lo2(swyt[x / 2]));
+    const float dm = fmaf(-m, a, bm), dt = fmaf(-m, at, bt);
+    swdd_l -= m * ((bm + dm) + (bt + dt));
+    swdf[x] = warp_sum(dm + dt);
+  }
+  const float swdd_w = warp_sum(swdd_l);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    gW[r] += __shfl_xor_sync(FULL, gW[r], 1);
+    gW[r] += __shfl_xor_sync(FULL, gW[r], 2);
+  }
+  sfr += __shfl_xor_sync(FULL, sfr, 1);
+  sfr += __shfl_xor_sync(FULL, sfr, 2);
+  sfo += __shfl_xor_sync(FULL, sfo, 1);
+  sfo += __shfl_xor_sync(FULL, sfo, 2);
+  ll2 += __shfl_xor_sync(FULL, ll2, 1);
+  ll2 += __shfl_xor_sync(FULL, ll2, 2);
+  // the tail statistics of marker jt are spread over the CPT cell groups of the tail pass
+  float swt_f[2 * NPT];
+#pragma unroll
+  for (int x = 0; x < 2 * NPT; ++x) {
+    float v = (x & 1) ? hi2(swt[x / 2]) : lo2(swt[x / 2]);
+#pragma unroll
+    for (int o = TP; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+    swt_f[x] = v;
+  }
+
+  float* mine = sred + warp * pl.total;
+  __syncthreads();            // every warp is done with the tiles and the Z tables
+  for (int t = lane; t < pl.total; t += 32) mine[t] = 0.f;
+  __syncwarp();
+#pragma unroll
+  for (int x = 0; x < NC; ++x) {
+    const float vm_ = (x & 1) ? hi2(swm[x / 2]) : lo2(swm[x / 2]);
+    const bool z1 = x >= LM0;
+    const int l = z1 ? x - LM0 : x;
+    if (l < (z1 ? L1 : L0)) {
+      const int base = (z1 ? pl.sw1 : pl.sw0) + l * J;
+      mine[base + lane] = vm_;
+      if (lane < TP && tail_ok) mine[base + jt] = swt_f[x];
+    }
+  }
+  // dZ fragments of n-tile `warp`: (mt, r) -> marker 6g + 2mt + (r >> 1), feature 8 warp + 2 t4 + (r & 1)
+#pragma unroll
+  for (int mt = 0; mt < kXMTJ; ++mt)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = 6 * g + 2 * mt + (r >> 1), k = 8 * warp + 2 * t4 + (r & 1);
+      if (j < J && k < K) mine[pl.dZ + k * J + j] = dZ[mt][r];
+    }
+  if (t4 == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int k = 16 * (r >> 1) + g + 8 * (r & 1);
+      if (k < K) mine[pl.gW + k] = gW[r];
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int x = 0; x < NC; ++x) {
+      if (x < LM0) { if (x < L0) mine[pl.swd0 + x] = swdf[x]; }
+      else if (x - LM0 < L1) mine[pl.swd1 + (x - LM0)] = swdf[x];
+    }
+    mine[pl.sc + 0] = swdd_w;
+    mine[pl.sc + 1] = sfr;
+    mine[pl.sc + 2] = sfo;
+    double* md = reinterpret_cast<double*>(mine + pl.dbl);
+    md[0] = (double)fac * (ll2 * 0.6931471805599453);
+    md[1] = 0.0;
+  }
+  __syncthreads();
+  float* out = p.partials + (size_t)blockIdx.x * pl.total;
+  for (int t = threadIdx.x; t < pl.total; t += kXThreads) {
+    if (t >= pl.dbl && t < pl.dbl + 4) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kXWarps; ++w) a += sred[w * pl.total + t];
+    out[t] = a;
+  }
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int w = 0; w < kXWarps; ++w) a += reinterpret_cast<const double*>(sred + w * pl.total + pl.dbl)[threadIdx.x];
+    reinterpret_cast<double*>(out + pl.dbl)[threadIdx.x] = a;
+  }
+}
+
+}  // namespace cytof

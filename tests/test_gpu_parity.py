@@ -52,10 +52,13 @@ def check_block(blk, ref, lay, tol=GRAD_TOL):
             assert rel(a, b) < tol, (n, rel(a, b))
 
 
-def run_kernel(eng, g, Z, rows_idx, eps, model_noisy, step=1):
+def run_kernel(eng, g, Z, rows_idx, eps, model_noisy, step=1, in_order=False):
     dev = eng.device
     counts = [len(ix) for ix in rows_idx]
     idx = torch.tensor(np.concatenate(rows_idx).astype(np.int32), device=dev) if sum(counts) else None
+    if in_order:      # every sample taken whole and in order: the kernels' no-index variants
+        assert all(np.array_equal(ix, np.arange(n)) for ix, n in zip(rows_idx, eng.N_local))
+        idx = None
     eps_t = None if eps is None else torch.tensor(np.concatenate(eps, 0), dtype=torch.float32, device=dev)
     batch = Batch(counts, idx, eps_t, step=step)
     blk, ll = eng.fwdbwd(batch, pack_globals(g, eng.I, model_noisy).to(dev), pack_zmask(Z).to(dev))
@@ -158,6 +161,34 @@ def test_kernel_random_shapes(shape, noisy):
     blk, ll, _ = run_kernel(eng, g, g['Z'], idx, eps, noisy)
     assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref)
     assert abs(ll[1] - lqy_ref) <= ELBO_TOL * max(1.0, abs(lqy_ref))
+    check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
+
+
+@pytest.mark.parametrize('shape', [
+    dict(I=2, J=40, K=50, L0=8, L1=8, N=[230, 117]),     # cfg5 shapes: one tail pass of 4 cells x 8 markers
+    dict(I=3, J=45, K=64, L0=5, L1=3, N=[64, 130, 33]),  # two tail passes of 2 cells x 16 markers, K at the maximum
+    dict(I=1, J=33, K=9, L0=2, L1=2, N=[301]),           # one tail marker, few features
+    dict(I=2, J=48, K=33, L0=8, L1=5, N=[97, 40]),       # J at the kernel's maximum
+])
+@pytest.mark.parametrize('noisy', [True, False])
+@pytest.mark.parametrize('gather', [True, False])
+def test_kernel_wide_shapes_without_missing(shape, noisy, gather):
+    """32 < J <= 48 without NaN: the tensor-core kernel with packed tail markers and CTA-cooperative
+    dZ (elbo_kernel_mma64.cuh) against the closed-form oracle; ragged tiles, gathered and in-order rows."""
+    I, J, K, L0, L1, N = (shape[k] for k in ('I', 'J', 'K', 'L0', 'L1', 'N'))
+    y, g = _random_problem(I, J, K, L0, L1, N, 0.0, seed=I * 1000 + J)
+    rng = np.random.default_rng(7)
+    idx = [rng.permutation(n)[:max(1, (3 * n) // 4)] for n in N] if gather else [np.arange(n) for n in N]
+    eps = [np.zeros((len(ix), J)) for ix in idx]
+    rows = [yi[ix] for yi, ix in zip(y, idx)]
+    fac = np.array([n / len(ix) for n, ix in zip(N, idx)])
+    ll_ref, lqy_ref, blk_ref, _ = ccf.cells_fwdbwd(rows, eps, g, fac, 1.0, np.sqrt(10.0), noisy)
+    eng = CellEngine([torch.tensor(t, dtype=torch.float32) for t in y], _dev(), K, L0, L1, noisy,
+                     float(np.sqrt(10.0)), 1.0, g['b'])
+    assert eng.no_missing
+    blk, ll, _ = run_kernel(eng, g, g['Z'], idx, None, noisy, in_order=not gather)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    assert ll[1] == 0.0 and lqy_ref == 0.0
     check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
 
 
