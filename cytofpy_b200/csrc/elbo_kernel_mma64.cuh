@@ -20,6 +20,9 @@
 
 namespace cytof {
 
+#ifndef CYTOF_X_NOGUARD
+#define CYTOF_X_NOGUARD 1   // 1 (measured faster): always run the full 4x6 / 3x8 MMA grids (padding is zero in the Z tables)
+#endif
 constexpr int kXThreads = 256;
 constexpr int kXWarps = kXThreads / 32;
 constexpr int kXT = 4;                    // cells per warp tile
@@ -245,37 +248,41 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
 
   float2 ee[NU][NPT];
 
-  // forward of unit `un` of the tile whose y rows are in `src`; writes the tiles of buffer `b`
-  auto phase_a = [&](const int un, const float* src, const int b) {
-    float* sD = sDb + b * (8 * kXDS);
-    float S0, S1, B0, B1;
+  // forward of unit `un` of the tile whose y rows are in `src`, in two halves: a1 issues the ex2 of
+  // the unit, a2 (called one unit later, so the MUFU pipe already works on the next exponentials
+  // while these sums settle) takes the logs / reciprocal and writes the tiles of buffer `b`
+  struct AState { float S0, S1, B0, B1, yv; };
+  auto phase_a1 = [&](const int un, const float* src) -> AState {
+    AState st;
     if (un < kXT) {                               // main pass: cell un, marker lane
-      const float yv = src[un * kXJS + lane];
-      mix_forward<LM0, NC, NPT>(yv, mc0, mc1, nh2, be, alm, ee[un], S0, S1, B0, B1);
-      const float A0 = B0 + fast_lg2(S0), A1 = B1 + fast_lg2(S1);
-      const float rr = fast_rcp(S0 * S1);
-      sR[un * 32 + lane] = make_float2(rr * S1, rr * S0);
-      uint32_t dh, dl;
+      st.yv = src[un * kXJS + lane];
+      mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, alm, ee[un], st.S0, st.S1, st.B0, st.B1);
+    } else {                                      // tail pass: cell cu, tail marker jt
+      const int cu = (un - kXT) * CPT + tcell;
+      st.yv = tail_ok ? src[cu * kXJS + jt] : 0.f;
+      mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, alt, ee[un], st.S0, st.S1, st.B0, st.B1);
+    }
+    return st;
+  };
+  auto phase_a2 = [&](const int un, const AState& st, const int b) {
+    float* sD = sDb + b * (8 * kXDS);
+    const float A0 = st.B0 + fast_lg2(st.S0), A1 = st.B1 + fast_lg2(st.S1);
+    const float rr = fast_rcp(st.S0 * st.S1);
+    sR[un * 32 + lane] = make_float2(rr * st.S1, rr * st.S0);
+    uint32_t dh, dl;
+    if (un < kXT) {
       split_tf32(A1 - A0, dh, dl);
       sD[(2 * un) * kXDS + lane] = __uint_as_float(dh);
       sD[(2 * un + 1) * kXDS + lane] = __uint_as_float(dl);
       sA[un * kXDS + lane] = A0;
-      if (NOISY) sY[un * kXDS + lane] = yv * yv;
-    } else {                                      // tail pass: cell cu, tail marker jt
+      if (NOISY) sY[un * kXDS + lane] = st.yv * st.yv;
+    } else {
       const int cu = (un - kXT) * CPT + tcell;
-      const float yv = tail_ok ? src[cu * kXJS + jt] : 0.f;
-      mix_forward<LM0, NC, NPT>(yv, mc0, mc1, nh2, be, alt, ee[un], S0, S1, B0, B1);
-      const float A0 = B0 + fast_lg2(S0), A1 = B1 + fast_lg2(S1);
-      const float rr = fast_rcp(S0 * S1);
-      sR[un * 32 + lane] = make_float2(rr * S1, rr * S0);
-      uint32_t dh, dl;
       split_tf32(tokf * (A1 - A0), dh, dl);
-      if (jt < kXJS) {
-        sD[(2 * cu) * kXDS + jt] = __uint_as_float(dh);
-        sD[(2 * cu + 1) * kXDS + jt] = __uint_as_float(dl);
-        sA[cu * kXDS + jt] = tokf * A0;
-        if (NOISY) sY[cu * kXDS + jt] = yv * yv;
-      }
+      sD[(2 * cu) * kXDS + jt] = __uint_as_float(dh);
+      sD[(2 * cu + 1) * kXDS + jt] = __uint_as_float(dl);
+      sA[cu * kXDS + jt] = tokf * A0;
+      if (NOISY) sY[cu * kXDS + jt] = st.yv * st.yv;
     }
   };
   auto phase_b = [&](const int un, const float* src) {
@@ -296,8 +303,16 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     issue_tile(0, 0);
     cp_async_wait<0>();
     __syncwarp();
+    {
+      AState prev = phase_a1(0, sYb);
 #pragma unroll
-    for (int un = 0; un < NU; ++un) phase_a(un, sYb, 0);
+      for (int un = 1; un < NU; ++un) {
+        const AState now = phase_a1(un, sYb);
+        phase_a2(un - 1, prev, 0);
+        prev = now;
+      }
+      phase_a2(NU - 1, prev, 0);
+    }
     if (nrounds > 1) issue_tile(1, 1);
   }
   __syncthreads();   // Z tables visible
@@ -329,10 +344,10 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       }
 #pragma unroll
       for (int c = 0; c < kXNCJ; ++c) {
-        if (c < ncj) {
+        if (CYTOF_X_NOGUARD || c < ncj) {
 #pragma unroll
           for (int mt = 0; mt < kXMTK; ++mt)
-            if (mt < mtk) mma_tf32(fT[mt], sZT[(mt * kXNCJ + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
+            if (CYTOF_X_NOGUARD || mt < mtk) mma_tf32(fT[mt], sZT[(mt * kXNCJ + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
         }
       }
     }
@@ -372,10 +387,10 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       for (int mt = 0; mt < kXMTJ; ++mt) cT[mt][0] = cT[mt][1] = cT[mt][2] = cT[mt][3] = 0.f;
 #pragma unroll
       for (int c = 0; c < kXNCK; ++c) {
-        if (c < nck) {
+        if (CYTOF_X_NOGUARD || c < nck) {
 #pragma unroll
           for (int mt = 0; mt < kXMTJ; ++mt)
-            if (mt < mtj) mma_tf32(cT[mt], sZ[(mt * kXNCK + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
+            if (CYTOF_X_NOGUARD || mt < mtj) mma_tf32(cT[mt], sZ[(mt * kXNCK + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
         }
       }
     }
@@ -472,11 +487,16 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       const float* ynxt = sYb + (b ^ 1) * (kXT * kXJS);
       cp_async_wait<0>();
       __syncwarp();
+      phase_b(0, ycur);
+      AState prev = phase_a1(0, ynxt);
 #pragma unroll
-      for (int un = 0; un < NU; ++un) {
+      for (int un = 1; un < NU; ++un) {
         phase_b(un, ycur);
-        phase_a(un, ynxt, b ^ 1);
+        const AState now = phase_a1(un, ynxt);
+        phase_a2(un - 1, prev, b ^ 1);
+        prev = now;
       }
+      phase_a2(NU - 1, prev, b ^ 1);
     } else {
 #pragma unroll
       for (int un = 0; un < NU; ++un) phase_b(un, ycur);
