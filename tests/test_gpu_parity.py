@@ -348,3 +348,50 @@ def test_full_size_properties_cfg4_shape():
     bb, l2 = eng.fwdbwd(Batch([250] * I, it, None, step=1), G, zm)
     assert abs(l2[0].item() - ll_ref) <= ELBO_TOL * abs(ll_ref)
     check_block(bb.cpu().numpy().astype(np.float64), blk_ref, lay)
+
+
+def test_full_size_properties_cfg5_shape():
+    """BASELINE cfg5 shape per-sample at a size the GPU does in milliseconds and the oracle cannot
+    (I=8 x 100,000 cells, J=40, K=50, L=8/8, no missing data -> elbo_kernel_mma64.cuh): additivity
+    over disjoint halves, permutation invariance, linearity in fac_i, bitwise reproducibility, and a
+    slice against the fp64 oracle."""
+    I, J, K, L0, L1 = 8, 40, 50, 8, 8
+    N = [100000] * I
+    dev = _dev()
+    s = cy.util.synth_cytof(N, J, [100.] * 5, L0, L1, seed=0)
+    _, g = _random_problem(I, J, K, L0, L1, [1] * I, 0.0, seed=41)
+    g['mu0'], g['mu1'] = -(np.arange(L0) * 0.7 + 1.5), np.arange(L1) * 0.7 + 1.5
+    y32 = [torch.from_numpy(a) for a in s['y']]
+    eng = CellEngine(y32, dev, K, L0, L1, True, float(np.sqrt(10.0)), 1.0, g['b'], seed=9)
+    assert eng.no_missing
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    lay = ccf.block_layout(I, J, K, L0, L1)
+    blk, ll = eng.fwdbwd(Batch(N, None, None, step=1), G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy().copy()
+    assert np.isfinite(blk).all() and np.isfinite(ll).all()
+    b2, l2 = eng.fwdbwd(Batch(N, None, None, step=1), G, zm)
+    assert np.array_equal(b2.cpu().numpy().astype(np.float64), blk) and l2[0].item() == ll[0]   # reproducible
+    tot_b, tot_l = 0, 0
+    for h in range(2):
+        idx = torch.cat([torch.arange(h * 50000, (h + 1) * 50000, dtype=torch.int32) for _ in range(I)]).to(dev)
+        bb, l2 = eng.fwdbwd(Batch([50000] * I, idx, None, step=1), G, zm, counts_global=N)
+        tot_b = tot_b + bb.cpu().numpy().astype(np.float64)
+        tot_l = tot_l + l2.cpu().numpy()
+    assert abs(tot_l[0] - ll[0]) <= 1e-7 * abs(ll[0])
+    check_block(tot_b, blk, lay, tol=2e-5)
+    gen = torch.Generator().manual_seed(0)
+    perm = torch.cat([torch.randperm(n, generator=gen).to(torch.int32) for n in N]).to(dev)
+    bb, l2 = eng.fwdbwd(Batch(N, perm, None, step=1), G, zm)
+    assert abs(l2[0].item() - ll[0]) <= 1e-7 * abs(ll[0])
+    check_block(bb.cpu().numpy().astype(np.float64), blk, lay, tol=2e-5)
+    bb, l2 = eng.fwdbwd(Batch(N, None, None, step=1), G, zm, counts_global=[n // 2 for n in N])
+    assert abs(l2[0].item() - 2 * ll[0]) <= 1e-9 * abs(ll[0])
+    check_block(bb.cpu().numpy().astype(np.float64), 2 * blk, lay, tol=1e-6)
+    idx = [np.arange(2000, 2150) for _ in range(I)]
+    rows = [s['y'][i][idx[i]].astype(np.float64) for i in range(I)]
+    fac = np.array([n / 150 for n in N])
+    ll_ref, _, blk_ref, _ = ccf.cells_fwdbwd(rows, [np.zeros((150, J))] * I, g, fac, 1.0, np.sqrt(10.0), True)
+    it = torch.tensor(np.concatenate(idx).astype(np.int32), device=dev)
+    bb, l2 = eng.fwdbwd(Batch([150] * I, it, None, step=1), G, zm)
+    assert abs(l2[0].item() - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    check_block(bb.cpu().numpy().astype(np.float64), blk_ref, lay)
