@@ -688,22 +688,25 @@ static const Variant kVariants[] = {
     CYTOF_VARIANT(3, 3, 2, 2), CYTOF_VARIANT(5, 5, 2, 2), CYTOF_VARIANT(8, 8, 2, 2),
 };
 
-// 32 < J <= 48, K <= 64, data without missing entries (cfg5): tensor-core kernel with CTA-cooperative
+// 32 < J <= 48, K <= 64 (cfg5): tensor-core kernel with CTA-cooperative
 // dZ (elbo_kernel_mma64.cuh).  fn index = noisy + 2 * has_idx + 4 * (tail passes - 1).
-#define CYTOF_VARIANT_MMA64(a, b) \
-  { a, b, 2, 2, kXWarpFloats, kXZFloats, { elbo_fwdbwd_mma64_kernel<a, b, false, false, 1>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 1>, \
-                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 1>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 1>, \
-                             elbo_fwdbwd_mma64_kernel<a, b, false, false, 2>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 2>, \
-                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 2>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 2> }, true, kXThreads }
+#define CYTOF_VARIANT_MMA64(a, b, miss) \
+  { a, b, 2, 2, kXWarpFloats, kXZFloats, { elbo_fwdbwd_mma64_kernel<a, b, false, false, 1, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 1, miss>, \
+                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 1, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 1, miss>, \
+                             elbo_fwdbwd_mma64_kernel<a, b, false, false, 2, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 2, miss>, \
+                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 2, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 2, miss> }, true, kXThreads }
 #ifndef CYTOF_MMA64
 #define CYTOF_MMA64 1
 #endif
-static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5), CYTOF_VARIANT_MMA64(8, 8) };
+// [0..1]: kernels without the imputation path (CYTOF_FLAG_NO_MISSING), [2..3]: with it
+static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5, false), CYTOF_VARIANT_MMA64(8, 8, false),
+                                       CYTOF_VARIANT_MMA64(5, 5, true), CYTOF_VARIANT_MMA64(8, 8, true) };
 static const Variant* pick_variant64(const cytof_desc* d) {
-  if (!CYTOF_MMA64 || !(d->flags & CYTOF_FLAG_NO_MISSING)) return nullptr;
+  if (!CYTOF_MMA64) return nullptr;
   if (d->J <= 32 || d->J > 48 || d->K > 64) return nullptr;
-  for (const Variant& v : kVariants64)
-    if (v.lm0 >= d->L0 && v.lm1 >= d->L1) return &v;
+  const int first = (d->flags & CYTOF_FLAG_NO_MISSING) ? 0 : 2;
+  for (int q = first; q < first + 2; ++q)
+    if (kVariants64[q].lm0 >= d->L0 && kVariants64[q].lm1 >= d->L1) return &kVariants64[q];
   return nullptr;
 }
 
@@ -749,7 +752,7 @@ static OccEntry g_occ[64][20][8] = {};
 static int variant_occupancy(const Variant* v, int fi, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
-  const bool is64 = v >= kVariants64 && v < kVariants64 + 2;
+  const bool is64 = v >= kVariants64 && v < kVariants64 + 4;
   OccEntry& e = g_occ[dev][is64 ? 16 + (int)(v - kVariants64) : (int)(v - kVariants)][fi];
   if (e.occ == 0 || e.smem != smem) {
     if (smem > 48 * 1024 && smem > e.smem_attr) {   // opt in to large dynamic shared memory

@@ -1,5 +1,5 @@
-// Tensor-core fused ELBO kernel for 32 < J <= 48 markers, K <= 64 features, L <= 8 components and
-// data without missing entries (BASELINE cfg5: J = 40, K = 50, L = 8/8).
+// Tensor-core fused ELBO kernel for 32 < J <= 48 markers, K <= 64 features, L <= 8 components
+// (BASELINE cfg5: J = 40, K = 50, L = 8/8).  MISSING = false compiles the imputation path out.
 //
 // The first SIMT kernel needs 1,767 warp-instructions per cell at these shapes (bit-mask Z gating,
 // two markers per lane, register spills; profiles/README.md).  This kernel keeps the structure of
@@ -33,8 +33,8 @@ constexpr int kXMTK = 4, kXMTJ = 3;       // m-tiles over features (64) and over
 constexpr int kXNCJ = 6, kXNCK = 8;       // k-chunks of 8 over markers and over features
 constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4;
 // per warp (floats): D hi/lo [2][8][52] | g hi/lo [2][8][68] | A0/c1 [4][52] | y^2 [4][52] |
-// 1/S0,1/S1 [6 units][32] float2 | per-cell scalars [16] | y double buffer [2][4][48]
-constexpr int kXWarpFloats = 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS + 6 * 32 * 2 + 16 + 2 * kXT * kXJS;
+// 1/S0,1/S1 [6 units][32] float2 | per-cell scalars [16] | y double buffer [2][4][48] | sum w d [6][32]
+constexpr int kXWarpFloats = 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS + 6 * 32 * 2 + 16 + 2 * kXT * kXJS + 6 * 32;
 
 template <int LM0, int NC, int NPT>
 __device__ __forceinline__ void mix_forward(const float yv, const float mc0, const float mc1, const float nh2,
@@ -69,27 +69,32 @@ __device__ __forceinline__ void mix_forward(const float yv, const float mc0, con
   B1 = fmaf(nh2 * y1, y1, M1);
 }
 
-template <int LM0, int NPT>
-__device__ __forceinline__ void mix_backward(const float yv, const float mc0, const float mc1, const float c0,
-                                             const float c1, const float2 rs01, const float2 (&ee)[NPT],
-                                             float2 (&sw)[NPT], float2 (&swy)[NPT], float& sq) {
+// returns sum_l w_l d_l = c0 y0' + c1 y1' - sum_l w_l mu'_l when WD (the imputation gradient needs it)
+template <int LM0, int NPT, bool WD>
+__device__ __forceinline__ float mix_backward(const float yv, const float mc0, const float mc1, const float c0,
+                                              const float c1, const float2 rs01, const float2 (&ee)[NPT],
+                                              const float2 (&mup)[NPT], float2 (&sw)[NPT], float2 (&swy)[NPT],
+                                              float& sq) {
   const float y0 = yv - mc0, y1 = yv - mc1;
   const float2 Y00 = bcp(y0), Y11 = bcp(y1), Y01 = mkp(y0, y1);
   const float r0 = c0 * rs01.x, r1 = c1 * rs01.y;
   const float2 R00 = bcp(r0), R11 = bcp(r1), R01 = mkp(r0, r1);
   sq = fmaf(c0 * y0, y0, fmaf(c1 * y1, y1, sq));
+  float2 wm = bcp(0.f);
 #pragma unroll
   for (int q = 0; q < NPT; ++q) {
     const bool lo1 = 2 * q >= LM0, hi1 = 2 * q + 1 >= LM0;
     const float2 w = mul2(lo1 ? R11 : (hi1 ? R01 : R00), ee[q]);
     acc_add2(sw[q], w);
     acc_fma2(swy[q], w, lo1 ? Y11 : (hi1 ? Y01 : Y00));
+    if (WD) acc_fma2(wm, w, mup[q]);
   }
+  return WD ? fmaf(c0, y0, c1 * y1) - (lo2(wm) + hi2(wm)) : 0.f;
 }
 
 // NTP = tail passes per 4-cell tile: 1 (J - 32 <= 8: 4 cells x 8 tail markers per pass) or
 //                                    2 (J - 32 <= 16: 2 cells x 16 tail markers per pass)
-template <int LM0, int LM1, bool NOISY, bool HAS_IDX, int NTP>
+template <int LM0, int LM1, bool NOISY, bool HAS_IDX, int NTP, bool MISSING>
 __global__ void __launch_bounds__(kXThreads, 1)
 elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;
@@ -110,6 +115,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   float2* sR = reinterpret_cast<float2*>(sY + kXT * kXDS);   // [NU][32] (1/S0, 1/S1) per unit and lane
   float* sS = reinterpret_cast<float*>(sR + 6 * 32);          // [0..3] fac rho, [4..7] fac (1-rho), [8..11] sc
   float* sYb = sS + 16;                            // [2][4][kXJS] y rows
+  float* sW = sYb + 2 * kXT * kXJS;                // [NU][32] sum_l w d per unit (imputation gradient)
   float* sred = smem;
 
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -191,8 +197,15 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     const int k = 16 * (r >> 1) + g + 8 * (r & 1);
     lwk[r] = k < K ? G[gl.lw + i * K + k] * kLog2e : kNegBig;
   }
-  float l1me2 = 0.f, zconst2 = 0.f, ninv2s2 = 0.f;
+  // imputation parameters of this lane's main marker and tail marker (vae.py:12-13), missingness b
+  const int jtl = tail_ok ? jt : 0;
+  const float vm_m = G[gl.vm + i * J + lane], vls_m = G[gl.vls + i * J + lane], sd_m = expf(vls_m);
+  const float vm_t = G[gl.vm + i * J + jtl], vls_t = G[gl.vls + i * J + jtl], sd_t = expf(vls_t);
+  const float b0 = G[gl.b + 3 * i], b1 = G[gl.b + 3 * i + 1], b2 = G[gl.b + 3 * i + 2];
+  const unsigned long long grow_base = (unsigned long long)p.row_global[i];
+  float l1me2 = 0.f, zconst2 = 0.f, ninv2s2 = 0.f, inv_s2n = 0.f;
   if (NOISY) {
+    inv_s2n = 1.0f / (p.noisy_sd * p.noisy_sd);
     const float e_i = G[gl.eps + i];
     l1me2 = log1pf(-e_i) * kLog2e;
     zconst2 = ((float)J * (-kHalfLog2Pi - logf(p.noisy_sd)) + logf(e_i)) * kLog2e;
@@ -205,6 +218,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   float dZ[kXMTJ][4];                    // n-tile `warp` of dZ, all 3 m-tiles (markers permuted, see epilogue)
   float gW[8];
   float sfr = 0.f, sfo = 0.f;
+  float dvm_m = 0.f, dvls_m = 0.f, nm_m = 0.f, dvm_t = 0.f, dvls_t = 0.f, nm_t = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
   double ll2 = 0.0;
 #pragma unroll
   for (int q = 0; q < NPT; ++q) swm[q] = swym[q] = swt[q] = swyt[q] = bcp(0.f);
@@ -246,20 +260,76 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     cp_async_commit();
   };
 
+  // imputation of missing entries (vae.py:17-33): NaNs of the tile in sYb[b] are replaced by the
+  // N(0,1) draw; mm = cells whose MAIN marker `lane` is missing, tm = tail passes whose entry of this
+  // lane is missing, am = units of the tile with any missing entry (warp-uniform)
+  auto prepass = [&](const int r, const int b, unsigned& mm, unsigned& tm, unsigned& am) {
+    const int tn = (r * kXWarps + warp) * kXT;
+    float* src = sYb + b * (kXT * kXJS);
+    mm = 0u;
+    tm = 0u;
+#pragma unroll
+    for (int u = 0; u < kXT; ++u) {
+      const float yr = src[u * kXJS + lane];
+      mm |= (yr != yr) ? (1u << u) : 0u;
+    }
+#pragma unroll
+    for (int ps = 0; ps < NTP; ++ps) {
+      const float yr = tail_ok ? src[(ps * CPT + tcell) * kXJS + jt] : 0.f;
+      tm |= (yr != yr) ? (1u << ps) : 0u;
+    }
+    am = __reduce_or_sync(FULL, mm | (tm << kXT));
+    if (am) {
+      unsigned long long grp_c = ~0ull;
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int u = 0; u < kXT; ++u) {
+        if (!((am >> u) & 1u)) continue;
+        const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+        float e = 0.f;
+        if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
+          if (p.eps) e = __ldg(p.eps + (cb + c_lo + tn + u) * J + lane);
+        } else {
+          const unsigned long long grow = grow_base + (unsigned long long)row;
+          if ((grow >> 2) != grp_c) {
+            grp_c = grow >> 2;
+            philox_normal4(p.seed, elbo_step(p), grp_c, lane, nz);
+          }
+          const unsigned w = (unsigned)grow & 3u;
+          e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));
+        }
+        if ((mm >> u) & 1u) src[u * kXJS + lane] = e;
+      }
+#pragma unroll 1
+      for (int ps = 0; ps < NTP; ++ps) {
+        if (!((am >> (kXT + ps)) & 1u)) continue;
+        const int cu = ps * CPT + tcell;
+        if ((tm >> ps) & 1u) {      // only lanes whose tail entry is NaN (it exists, so the cell is in range)
+          const int row = HAS_IDX ? __ldg(idx + tn + cu) : first_row + tn + cu;
+          src[cu * kXJS + jt] = p.noise_mode == CYTOF_NOISE_EXTERNAL
+                                    ? (p.eps ? __ldg(p.eps + (cb + c_lo + tn + cu) * J + jt) : 0.f)
+                                    : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)row, jt);
+        }
+      }
+    }
+  };
+
   float2 ee[NU][NPT];
 
   // forward of unit `un` of the tile whose y rows are in `src`, in two halves: a1 issues the ex2 of
   // the unit, a2 (called one unit later, so the MUFU pipe already works on the next exponentials
   // while these sums settle) takes the logs / reciprocal and writes the tiles of buffer `b`
   struct AState { float S0, S1, B0, B1, yv; };
-  auto phase_a1 = [&](const int un, const float* src) -> AState {
+  auto phase_a1 = [&](const int un, const float* src, const unsigned mm, const unsigned tm) -> AState {
     AState st;
     if (un < kXT) {                               // main pass: cell un, marker lane
-      st.yv = src[un * kXJS + lane];
+      const float x = src[un * kXJS + lane];
+      st.yv = (MISSING && ((mm >> un) & 1u)) ? fmaf(sd_m, x, vm_m) : x;
       mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, alm, ee[un], st.S0, st.S1, st.B0, st.B1);
     } else {                                      // tail pass: cell cu, tail marker jt
       const int cu = (un - kXT) * CPT + tcell;
-      st.yv = tail_ok ? src[cu * kXJS + jt] : 0.f;
+      const float x = tail_ok ? src[cu * kXJS + jt] : 0.f;
+      st.yv = (MISSING && ((tm >> (un - kXT)) & 1u)) ? fmaf(sd_t, x, vm_t) : x;
       mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, alt, ee[un], st.S0, st.S1, st.B0, st.B1);
     }
     return st;
@@ -282,32 +352,65 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       sD[(2 * cu) * kXDS + jt] = __uint_as_float(dh);
       sD[(2 * cu + 1) * kXDS + jt] = __uint_as_float(dl);
       sA[cu * kXDS + jt] = tokf * A0;
-      if (NOISY) sY[cu * kXDS + jt] = st.yv * st.yv;
+      if (NOISY) sY[cu * kXDS + jt] = tokf * st.yv * st.yv;
     }
   };
-  auto phase_b = [&](const int un, const float* src) {
+  auto phase_b = [&](const int un, const float* src, const unsigned mm, const unsigned tm, const unsigned am) {
     if (un < kXT) {
       const float c1 = sA[un * kXDS + lane];
       const float c0 = sS[un] - c1;
-      mix_backward<LM0, NPT>(src[un * kXJS + lane], mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], swm, swym, sq);
+      const float x = src[un * kXJS + lane];
+      const float yv = (MISSING && ((mm >> un) & 1u)) ? fmaf(sd_m, x, vm_m) : x;
+      const float wd = mix_backward<LM0, NPT, MISSING>(yv, mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], mup, swm, swym, sq);
+      if (MISSING && am) sW[un * 32 + lane] = wd;
     } else {
       const int cu = (un - kXT) * CPT + tcell;
       const float c1 = tail_ok ? sA[cu * kXDS + jt] : 0.f;
       const float c0 = tokf * sS[cu] - c1;
-      const float yv = tail_ok ? src[cu * kXJS + jt] : 0.f;
-      mix_backward<LM0, NPT>(yv, mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], swt, swyt, sq);
+      const float x = tail_ok ? src[cu * kXJS + jt] : 0.f;
+      const float yv = (MISSING && ((tm >> (un - kXT)) & 1u)) ? fmaf(sd_t, x, vm_t) : x;
+      const float wd = mix_backward<LM0, NPT, MISSING>(yv, mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], mup, swt, swyt, sq);
+      if (MISSING && am) sW[un * 32 + lane] = wd;
     }
   };
+  // logistic missingness (Model.py:269-274) and the d/dy chain into the imputation parameters of
+  // unit `un`, branch-free (lanes without a missing entry add 0)
+  auto missing_unit = [&](const int un, const float* src, const unsigned mm, const unsigned tm, const int tn) {
+    const bool main = un < kXT;
+    const int cu = main ? un : (un - kXT) * CPT + tcell;
+    const bool miss = main ? ((mm >> un) & 1u) : ((tm >> (un - kXT)) & 1u);
+    const bool vu = tn + cu < ncell;
+    const float mf = (miss && vu) ? 1.f : 0.f;
+    const float x = main ? src[un * kXJS + lane] : (tail_ok ? src[cu * kXJS + jt] : 0.f);
+    const float sd = main ? sd_m : sd_t, vm = main ? vm_m : vm_t, vls = main ? vls_m : vls_t;
+    const float e = miss ? x : 0.f;
+    const float yv = miss ? fmaf(sd, e, vm) : x;
+    const float fu = vu ? fac : 0.f;
+    const float uu = fmaf(fmaf(b2, yv, b1), yv, b0);
+    const float tmm = fast_ex2(-fabsf(uu) * kLog2e);
+    const float rr = fast_rcp(1.f + tmm);
+    const float ls = -(fmaxf(-uu, 0.f) + kLn2 * fast_lg2(1.f + tmm));
+    const float sneg = (uu > 0.f ? tmm : 1.f) * rr;   // 1 - sigmoid(u)
+    float dy = -sW[un * 32 + lane] * inv_sig2 + fu * sneg * fmaf(2.f * b2, yv, b1);
+    if (NOISY) dy = fmaf(-sS[4 + cu] * inv_s2n, yv, dy);
+    dy = miss ? dy : 0.f;
+    lmiss_l = fmaf(ls, mf, lmiss_l);
+    lqy_l = fmaf(fmaf(-0.5f * e, e, -vls - kHalfLog2Pi), mf, lqy_l);
+    if (main) { dvm_m += dy; dvls_m = fmaf(dy * sd, e, dvls_m); nm_m += mf; }
+    else { dvm_t += dy; dvls_t = fmaf(dy * sd, e, dvls_t); nm_t += mf; }
+  };
 
+  unsigned mmask = 0u, tmask = 0u, amask = 0u;
   if (nrounds > 0) {
     issue_tile(0, 0);
     cp_async_wait<0>();
     __syncwarp();
+    if (MISSING) prepass(0, 0, mmask, tmask, amask);
     {
-      AState prev = phase_a1(0, sYb);
+      AState prev = phase_a1(0, sYb, mmask, tmask);
 #pragma unroll
       for (int un = 1; un < NU; ++un) {
-        const AState now = phase_a1(un, sYb);
+        const AState now = phase_a1(un, sYb, mmask, tmask);
         phase_a2(un - 1, prev, 0);
         prev = now;
       }
@@ -483,24 +586,33 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
 
     // ===== backward of this round's tile, interleaved unit by unit with the forward of the next
     const float* ycur = sYb + b * (kXT * kXJS);
+    unsigned mm_n = 0u, tm_n = 0u, am_n = 0u;
     if (r + 1 < nrounds) {
       const float* ynxt = sYb + (b ^ 1) * (kXT * kXJS);
       cp_async_wait<0>();
       __syncwarp();
-      phase_b(0, ycur);
-      AState prev = phase_a1(0, ynxt);
+      if (MISSING) prepass(r + 1, b ^ 1, mm_n, tm_n, am_n);
+      phase_b(0, ycur, mmask, tmask, amask);
+      AState prev = phase_a1(0, ynxt, mm_n, tm_n);
 #pragma unroll
       for (int un = 1; un < NU; ++un) {
-        phase_b(un, ycur);
-        const AState now = phase_a1(un, ynxt);
+        phase_b(un, ycur, mmask, tmask, amask);
+        const AState now = phase_a1(un, ynxt, mm_n, tm_n);
         phase_a2(un - 1, prev, b ^ 1);
         prev = now;
       }
       phase_a2(NU - 1, prev, b ^ 1);
     } else {
 #pragma unroll
-      for (int un = 0; un < NU; ++un) phase_b(un, ycur);
+      for (int un = 0; un < NU; ++un) phase_b(un, ycur, mmask, tmask, amask);
     }
+    if (MISSING && amask) {
+#pragma unroll
+      for (int un = 0; un < NU; ++un) missing_unit(un, ycur, mmask, tmask, t0);
+    }
+    mmask = mm_n;
+    tmask = tm_n;
+    amask = am_n;
     __syncwarp();
     if (r + 2 < nrounds) issue_tile(r + 2, b);
   }
@@ -533,6 +645,14 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   sfo += __shfl_xor_sync(FULL, sfo, 2);
   ll2 += __shfl_xor_sync(FULL, ll2, 1);
   ll2 += __shfl_xor_sync(FULL, ll2, 2);
+  lqy_l = warp_sum(lqy_l);
+  lmiss_l = warp_sum(lmiss_l);
+#pragma unroll
+  for (int o = TP; o < 32; o <<= 1) {
+    dvm_t += __shfl_xor_sync(FULL, dvm_t, o);
+    dvls_t += __shfl_xor_sync(FULL, dvls_t, o);
+    nm_t += __shfl_xor_sync(FULL, nm_t, o);
+  }
   // the tail statistics of marker jt are spread over the CPT cell groups of the tail pass
   float swt_f[2 * NPT];
 #pragma unroll
@@ -556,6 +676,16 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       const int base = (z1 ? pl.sw1 : pl.sw0) + l * J;
       mine[base + lane] = vm_;
       if (lane < TP && tail_ok) mine[base + jt] = swt_f[x];
+    }
+  }
+  if (MISSING) {
+    mine[pl.dvm + lane] = dvm_m;
+    mine[pl.dvls + lane] = dvls_m;
+    mine[pl.nm + lane] = nm_m;
+    if (lane < TP && tail_ok) {
+      mine[pl.dvm + jt] = dvm_t;
+      mine[pl.dvls + jt] = dvls_t;
+      mine[pl.nm + jt] = nm_t;
     }
   }
   // dZ fragments of n-tile `warp`: (mt, r) -> marker 6g + 2mt + (r >> 1), feature 8 warp + 2 t4 + (r & 1)
@@ -583,8 +713,8 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     mine[pl.sc + 1] = sfr;
     mine[pl.sc + 2] = sfo;
     double* md = reinterpret_cast<double*>(mine + pl.dbl);
-    md[0] = (double)fac * (ll2 * 0.6931471805599453);
-    md[1] = 0.0;
+    md[0] = (double)fac * (ll2 * 0.6931471805599453 + (double)lmiss_l);
+    md[1] = (double)fac * (double)p.scale * (double)lqy_l;
   }
   __syncthreads();
   float* out = p.partials + (size_t)blockIdx.x * pl.total;
