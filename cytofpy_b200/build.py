@@ -10,9 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, '_C')
 LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200.so')
-SOURCES = ['elbo_kernel.cu', 'global_part.cu', 'labels.cu', 'abi.cu']
+# same sources with the dZ accumulation on tcgen05.mma + TMEM (csrc/elbo_kernel_mma.cuh, CYTOF_TMEM_DZ):
+# measured 5 % slower than the default at cfg4, kept as a tested variant (tests/test_gpu_tmem_variant.py)
+TMEM_LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200_tmem.so')
+SOURCES = ['variants_mma64.cu', 'variants_mma.cu', 'elbo_kernel.cu', 'global_part.cu', 'labels.cu', 'abi.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC']
 
 
 def _nvcc():
@@ -22,10 +25,11 @@ def _nvcc():
     raise RuntimeError('nvcc not found (set NVCC=/path/to/nvcc)')
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
+def _stale(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(HERE, '..', 'include', 'cytof_b200.h'))
     return any(os.path.getmtime(d) > t for d in deps)
@@ -38,14 +42,34 @@ def build(force=False, verbose=False, defines=(), out=None):
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     target = out or LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-D' + d for d in defines] + ['-o', target] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # one object per translation unit, compiled in parallel (the template-heavy ones take ~1 min each)
+    obj_dir = os.path.join(OUT_DIR, 'obj_' + os.path.splitext(os.path.basename(target))[0])
+    os.makedirs(obj_dir, exist_ok=True)
+    base = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-D' + d for d in defines]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + '.o')
+        r = subprocess.run(base + ['-c', '-o', obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        return src, obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for src, obj, r in results:
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed on %s:\n' % src + r.stdout + r.stderr)
+        if verbose:
+            sys.stderr.write(r.stderr)
+    r = subprocess.run([_nvcc(), '-shared', '-o', target] + [obj for _, obj, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
     return target
+
+
+def build_tmem_variant(force=False):
+    if not force and not _stale(TMEM_LIB_PATH):
+        return TMEM_LIB_PATH
+    return build(defines=['CYTOF_TMEM_DZ=1'], out=TMEM_LIB_PATH)
 
 
 if __name__ == '__main__':

@@ -200,6 +200,14 @@ struct ElboParams {
   int blk_begin[CYTOF_MAX_SAMPLES + 1];
 };
 
+// The heavy template instantiations live in their own translation units (variants_mma.cu,
+// variants_mma64.cu) so that the library builds in parallel; elbo_kernel.cu asks for the kernels.
+using KernelFn = void (*)(const ElboParams);
+// lidx: 0 = (3,3), 1 = (5,3), 2 = (5,5), 3 = (8,8) mixture sizes; fi = noisy + 2 * has_idx + 4 * no_missing
+KernelFn mma_kernel_fn(int lidx, int fi);
+// lidx: 0 = (5,5), 1 = (8,8); missing: imputation path compiled in; fi = noisy + 2 * has_idx + 4 * (tail passes - 1)
+KernelFn mma64_kernel_fn(int lidx, int missing, int fi);
+
 __device__ __forceinline__ uint32_t elbo_step(const ElboParams& p) {
   return p.step_dev ? (uint32_t)(*p.step_dev + 1) : p.step;
 }

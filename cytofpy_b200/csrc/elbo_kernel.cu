@@ -635,8 +635,6 @@ __global__ void impute_emit_kernel(const ElboParams p, float* __restrict__ eps_o
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
-using KernelFn = void (*)(const ElboParams);
-
 struct Variant {
   int lm0, lm1, jp, kp;
   int smem_floats_per_warp, smem_floats_extra;
@@ -655,11 +653,10 @@ static int variant_threads(const Variant* v) { return v->threads ? v->threads : 
                              elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true>, \
                              elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
                              elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true> } }
-#define CYTOF_VARIANT_MMA(a, b) \
-  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma_kernel<a, b, false, false, true>, elbo_fwdbwd_mma_kernel<a, b, true, false, true>, \
-                             elbo_fwdbwd_mma_kernel<a, b, false, true, true>, elbo_fwdbwd_mma_kernel<a, b, true, true, true>, \
-                             elbo_fwdbwd_mma_kernel<a, b, false, false, false>, elbo_fwdbwd_mma_kernel<a, b, true, false, false>, \
-                             elbo_fwdbwd_mma_kernel<a, b, false, true, false>, elbo_fwdbwd_mma_kernel<a, b, true, true, false> }, true }
+#define CYTOF_FN8(f, ...) { f(__VA_ARGS__, 0), f(__VA_ARGS__, 1), f(__VA_ARGS__, 2), f(__VA_ARGS__, 3), \
+                            f(__VA_ARGS__, 4), f(__VA_ARGS__, 5), f(__VA_ARGS__, 6), f(__VA_ARGS__, 7) }
+#define CYTOF_VARIANT_MMA(a, b, lidx) \
+  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, CYTOF_FN8(mma_kernel_fn, lidx), true }
 #define CYTOF_VARIANT_MMA4(a, b) \
   { a, b, 1, 1, kQWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma4_kernel<a, b, false, false, true>, elbo_fwdbwd_mma4_kernel<a, b, true, false, true>, \
                              elbo_fwdbwd_mma4_kernel<a, b, false, true, true>, elbo_fwdbwd_mma4_kernel<a, b, true, true, true>, \
@@ -677,7 +674,7 @@ static const Variant kVariants[] = {
 #if CYTOF_MMA == 2
     CYTOF_VARIANT_MMA4(3, 3), CYTOF_VARIANT_MMA4(5, 3), CYTOF_VARIANT_MMA4(5, 5), CYTOF_VARIANT_MMA4(8, 8),
 #elif CYTOF_MMA
-    CYTOF_VARIANT_MMA(3, 3), CYTOF_VARIANT_MMA(5, 3), CYTOF_VARIANT_MMA(5, 5), CYTOF_VARIANT_MMA(8, 8),
+    CYTOF_VARIANT_MMA(3, 3, 0), CYTOF_VARIANT_MMA(5, 3, 1), CYTOF_VARIANT_MMA(5, 5, 2), CYTOF_VARIANT_MMA(8, 8, 3),
 #elif CYTOF_J32
     CYTOF_VARIANT_J32(3, 3), CYTOF_VARIANT_J32(4, 3), CYTOF_VARIANT_J32(5, 3),
     CYTOF_VARIANT_J32(5, 5), CYTOF_VARIANT_J32(8, 8),
@@ -690,17 +687,14 @@ static const Variant kVariants[] = {
 
 // 32 < J <= 48, K <= 64 (cfg5): tensor-core kernel with CTA-cooperative
 // dZ (elbo_kernel_mma64.cuh).  fn index = noisy + 2 * has_idx + 4 * (tail passes - 1).
-#define CYTOF_VARIANT_MMA64(a, b, miss) \
-  { a, b, 2, 2, kXWarpFloats, kXZFloats, { elbo_fwdbwd_mma64_kernel<a, b, false, false, 1, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 1, miss>, \
-                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 1, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 1, miss>, \
-                             elbo_fwdbwd_mma64_kernel<a, b, false, false, 2, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 2, miss>, \
-                             elbo_fwdbwd_mma64_kernel<a, b, false, true, 2, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 2, miss> }, true, kXThreads }
+#define CYTOF_VARIANT_MMA64(a, b, lidx, miss) \
+  { a, b, 2, 2, kXWarpFloats, kXZFloats, CYTOF_FN8(mma64_kernel_fn, lidx, miss), true, kXThreads }
 #ifndef CYTOF_MMA64
 #define CYTOF_MMA64 1
 #endif
 // [0..1]: kernels without the imputation path (CYTOF_FLAG_NO_MISSING), [2..3]: with it
-static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5, false), CYTOF_VARIANT_MMA64(8, 8, false),
-                                       CYTOF_VARIANT_MMA64(5, 5, true), CYTOF_VARIANT_MMA64(8, 8, true) };
+static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5, 0, 0), CYTOF_VARIANT_MMA64(8, 8, 1, 0),
+                                       CYTOF_VARIANT_MMA64(5, 5, 0, 1), CYTOF_VARIANT_MMA64(8, 8, 1, 1) };
 static const Variant* pick_variant64(const cytof_desc* d) {
   if (!CYTOF_MMA64) return nullptr;
   if (d->J <= 32 || d->J > 48 || d->K > 64) return nullptr;

@@ -1,0 +1,18 @@
+// Instantiations of the tensor-core kernel for 32 < J <= 48, K <= 64 (csrc/elbo_kernel_mma64.cuh).
+#include "elbo_kernel_mma64.cuh"
+
+namespace cytof {
+
+#define CYTOF_MMA64_ROW(a, b, miss) \
+  { elbo_fwdbwd_mma64_kernel<a, b, false, false, 1, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 1, miss>, \
+    elbo_fwdbwd_mma64_kernel<a, b, false, true, 1, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 1, miss>, \
+    elbo_fwdbwd_mma64_kernel<a, b, false, false, 2, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, false, 2, miss>, \
+    elbo_fwdbwd_mma64_kernel<a, b, false, true, 2, miss>, elbo_fwdbwd_mma64_kernel<a, b, true, true, 2, miss> }
+
+KernelFn mma64_kernel_fn(int lidx, int missing, int fi) {
+  static const KernelFn table[2][2][8] = { { CYTOF_MMA64_ROW(5, 5, false), CYTOF_MMA64_ROW(5, 5, true) },
+                                           { CYTOF_MMA64_ROW(8, 8, false), CYTOF_MMA64_ROW(8, 8, true) } };
+  return table[lidx][missing][fi];
+}
+
+}  // namespace cytof
