@@ -11,10 +11,13 @@
 //     instead of 62 % with "two markers per lane";
 //   * Z^T . D^T is 4 m-tiles x ceil(J/8) k-chunks, Z . e^T is 3 m-tiles x ceil(K/8) k-chunks;
 //   * dZ (48 x 64) would be 96 accumulator registers per thread if every warp kept its own copy.
-//     Instead the CTA works in ROUNDS of 8 tiles: after the contraction stage of a round every
-//     warp's D and g tiles are in shared memory, one __syncthreads, and warp w accumulates the
-//     n-tile w of dZ (features 8w..8w+7, all markers: 12 registers) over the tiles of ALL warps.
-//     The tiles are double-buffered, so one barrier per round suffices.
+//     Instead the CTA works in ROUNDS of 8 tiles and dZ lives in TENSOR MEMORY: every warp pair
+//     writes the hi / lo split of its D and g values into K-major operand tiles (8 cells = K), one
+//     __syncthreads, and one thread issues 4 tcgen05.mma.kind::tf32 (M = N = 128 = hi | lo rows,
+//     K = 8) into the ONE 128 x 128 fp32 accumulator of the CTA in TMEM (fixed order: reproducible);
+//     tcgen05.commit -> mbarrier tells when the double-buffered operand tiles may be rewritten, and
+//     the epilogue reads the accumulator with tcgen05.ld.  (-DCYTOF_X_TMEM=0: the same with mma.sync,
+//     warp w accumulating n-tile w over the tiles of all warps -- 5 % slower.)
 #pragma once
 #include "elbo_kernel_mma4.cuh"
 
@@ -31,7 +34,15 @@ constexpr int kXGS = 68;                  // row stride of the e / g tile (64 fe
 constexpr int kXJS = 48;                  // row stride of the y buffer
 constexpr int kXMTK = 4, kXMTJ = 3;       // m-tiles over features (64) and over markers (48)
 constexpr int kXNCJ = 6, kXNCK = 8;       // k-chunks of 8 over markers and over features
-constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4;
+#ifndef CYTOF_X_TMEM
+#define CYTOF_X_TMEM 1   // 1: dZ on tcgen05.mma + TMEM (one 128 x 128 accumulator per CTA); 0: CTA-cooperative mma.sync
+#endif
+// CTA-level region after the Z tables (CYTOF_X_TMEM): header (2 mbarriers, TMEM base) and the operand
+// tiles of the 4 warp PAIRS, double-buffered: A = [D_hi (64 rows) ; D_lo (64 rows)] x 8 cells, B = [g_hi ; g_lo]
+constexpr int kXUFloats = CYTOF_X_TMEM ? 16 + 4 * 2 * 2 * 1024 : 0;
+constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4 + kXUFloats;
+// c = F32, a = b = TF32, both K-major, N = 128, M = 128
+constexpr uint32_t kUmmaIdesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 // per warp (floats): D hi/lo [2][8][52] | g hi/lo [2][8][68] | A0/c1 [4][52] | y^2 [4][52] |
 // 1/S0,1/S1 [6 units][32] float2 | per-cell scalars [16] | y double buffer [2][4][48] | sum w d [6][32]
 constexpr int kXWarpFloats = 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS + 6 * 32 * 2 + 16 + 2 * kXT * kXJS + 6 * 32;
@@ -106,7 +117,14 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   const int g = lane >> 2, t4 = lane & 3;
   uint4* sZT = reinterpret_cast<uint4*>(smem);              // [mt < 4][c < 6][lane]  A fragments of Z^T (k x j)
   uint4* sZ = sZT + kXMTK * kXNCJ * 32;                     // [mt < 3][c < 8][lane]  A fragments of Z   (j x k)
-  float* wbase0 = smem + kXZFloats;
+  float* wbase0 = smem + kXZFloats;      // kXZFloats includes the CTA-level operand region
+#if CYTOF_X_TMEM
+  float* uhdr = smem + (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4;
+  unsigned long long* xbar = reinterpret_cast<unsigned long long*>(uhdr);          // [2] one mbarrier per buffer
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(uhdr + 4);
+  unsigned char* sU = reinterpret_cast<unsigned char*>(uhdr + 16);                  // [pair][buf][A | B][4096 B]
+  unsigned char* myU = sU + (warp >> 1) * (2 * 2 * 4096);                           // this warp pair's tiles
+#endif
   float* wbase = wbase0 + warp * kXWarpFloats;
   float* sDb = wbase;                              // [2][8][kXDS] row 2c = hi(D) of cell c, 2c+1 = lo(D)
   float* sGb = sDb + 2 * 8 * kXDS;                 // [2][8][kXGS] e, then g = fac rho softmax: hi / lo rows
@@ -147,6 +165,17 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     (second ? sZ : sZT)[mc * 32 + ln] = make_uint4(v[0], v[1], v[2], v[3]);
   }
   for (int e = lane; e < 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS; e += 32) wbase[e] = 0.f;   // D, g, A0, y^2 tiles
+#if CYTOF_X_TMEM
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(xbar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(xbar + 1)) : "memory");
+  }
+  for (int e = threadIdx.x; e < 4 * 2 * 2 * 1024; e += kXThreads) reinterpret_cast<float*>(sU)[e] = 0.f;   // pad rows stay zero
+#endif
 
   // ---------------- per-sample constants ----------------
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
@@ -215,17 +244,21 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   // ---------------- accumulators ----------------
   float2 swm[NPT], swym[NPT], swt[NPT], swyt[NPT];
   float sq = 0.f;                        // sum c_z y_z'^2 over all of this lane's units
+#if !CYTOF_X_TMEM
   float dZ[kXMTJ][4];                    // n-tile `warp` of dZ, all 3 m-tiles (markers permuted, see epilogue)
+#endif
   float gW[8];
   float sfr = 0.f, sfo = 0.f;
   float dvm_m = 0.f, dvls_m = 0.f, nm_m = 0.f, dvm_t = 0.f, dvls_t = 0.f, nm_t = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
   double ll2 = 0.0;
 #pragma unroll
   for (int q = 0; q < NPT; ++q) swm[q] = swym[q] = swt[q] = swyt[q] = bcp(0.f);
+#if !CYTOF_X_TMEM
 #pragma unroll
   for (int a = 0; a < kXMTJ; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) dZ[a][c] = 0.f;
+#endif
 #pragma unroll
   for (int r = 0; r < 8; ++r) gW[r] = 0.f;
 
@@ -334,6 +367,9 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     }
     return st;
   };
+#if CYTOF_X_TMEM
+  float udh[kXT], udl[kXT];    // hi / lo of D of the 4 cells of the tile: one 16-byte store each into the A operand tile
+#endif
   auto phase_a2 = [&](const int un, const AState& st, const int b) {
     float* sD = sDb + b * (8 * kXDS);
     const float A0 = st.B0 + fast_lg2(st.S0), A1 = st.B1 + fast_lg2(st.S1);
@@ -346,6 +382,15 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       sD[(2 * un + 1) * kXDS + lane] = __uint_as_float(dl);
       sA[un * kXDS + lane] = A0;
       if (NOISY) sY[un * kXDS + lane] = st.yv * st.yv;
+#if CYTOF_X_TMEM
+      udh[un] = __uint_as_float(dh);
+      udl[un] = __uint_as_float(dl);
+      if (un == kXT - 1) {     // A operand: row = marker (hi) / 64 + marker (lo), k = 4 (warp & 1) + cell
+        unsigned char* ua = myU + b * (2 * 4096) + (lane >> 3) * 256 + (warp & 1) * 128 + (lane & 7) * 16;
+        *reinterpret_cast<float4*>(ua) = make_float4(udh[0], udh[1], udh[2], udh[3]);
+        *reinterpret_cast<float4*>(ua + 2048) = make_float4(udl[0], udl[1], udl[2], udl[3]);
+      }
+#endif
     } else {
       const int cu = (un - kXT) * CPT + tcell;
       split_tf32(tokf * (A1 - A0), dh, dl);
@@ -353,6 +398,13 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       sD[(2 * cu + 1) * kXDS + jt] = __uint_as_float(dl);
       sA[cu * kXDS + jt] = tokf * A0;
       if (NOISY) sY[cu * kXDS + jt] = tokf * st.yv * st.yv;
+#if CYTOF_X_TMEM
+      {
+        unsigned char* ua = myU + b * (2 * 4096) + (jt >> 3) * 256 + (warp & 1) * 128 + (jt & 7) * 16 + cu * 4;
+        *reinterpret_cast<float*>(ua) = __uint_as_float(dh);
+        *reinterpret_cast<float*>(ua + 2048) = __uint_as_float(dl);
+      }
+#endif
     }
   };
   auto phase_b = [&](const int un, const float* src, const unsigned mm, const unsigned tm, const unsigned am) {
@@ -419,6 +471,11 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     if (nrounds > 1) issue_tile(1, 1);
   }
   __syncthreads();   // Z tables visible
+#if CYTOF_X_TMEM
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = *tmem_base_s;
+  bool umma_ok = true;
+#endif
 
   for (int r = 0; r < nrounds; ++r) {
     const int b = r & 1;
@@ -551,6 +608,40 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       if (j0 < kXJS) sA[t4 * kXDS + j0] = sc * (cT[mt][0] + cT[mt][1]);
       if (j0 + 8 < kXJS) sA[t4 * kXDS + j0 + 8] = sc * (cT[mt][2] + cT[mt][3]);
     }
+#if CYTOF_X_TMEM
+    // ===== contraction 3 on tcgen05 + TMEM: g = sc e, split, into the B operand tile of this warp pair
+    // (row = feature (hi) / 64 + feature (lo), k = 4 (warp & 1) + cell t4); after the CTA barrier one
+    // thread issues the 4 pair MMAs (TF32, M = N = 128, K = 8) of the round into the ONE accumulator of
+    // the CTA -- a fixed issue order, so the sums are reproducible.  (Measured: per-pair accumulators
+    // with pair barriers instead of the CTA barrier are 5 % slower.)
+    {
+      unsigned char* ub = myU + b * (2 * 4096) + 4096 + (warp & 1) * 128 + g * 16 + t4 * 4;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float gv = sc * ex[q];
+        gW[q] += gv;
+        uint32_t gh, gl2;
+        split_tf32(gv, gh, gl2);
+        *reinterpret_cast<float*>(ub + q * 256) = __uint_as_float(gh);            // feature 16 (q >> 1) + 8 (q & 1) + g
+        *reinterpret_cast<float*>(ub + q * 256 + 2048) = __uint_as_float(gl2);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // the operand tiles of ALL warp pairs for this round are complete
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const unsigned char* t = sU + pr * (2 * 2 * 4096) + b * (2 * 4096);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_acc), "l"(umma_desc_kmajor(t)), "l"(umma_desc_kmajor(t + 4096)), "r"(kUmmaIdesc128),
+                        "r"((r > 0 || pr > 0) ? 1u : 0u) : "memory");
+      }
+      umma_commit(xbar + b);
+    }
+#else
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float gv = sc * ex[q];
@@ -584,9 +675,15 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       }
     }
 
+#endif
+
     // ===== backward of this round's tile, interleaved unit by unit with the forward of the next
     const float* ycur = sYb + b * (kXT * kXJS);
     unsigned mm_n = 0u, tm_n = 0u, am_n = 0u;
+#if CYTOF_X_TMEM
+    // the next round's operands go to buffer b ^ 1: the MMAs of round r - 1 (same buffer) must be done
+    if (r + 1 < nrounds && r >= 1) umma_ok = mbar_wait(xbar + (b ^ 1), (uint32_t)(((r + 1) >> 1) - 1) & 1u) && umma_ok;
+#endif
     if (r + 1 < nrounds) {
       const float* ynxt = sYb + (b ^ 1) * (kXT * kXJS);
       cp_async_wait<0>();
@@ -664,7 +761,16 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   }
 
   float* mine = sred + warp * pl.total;
+#if CYTOF_X_TMEM
+  // the MMAs of the last two rounds have completed (=> all of them)
+  if (nrounds >= 1) umma_ok = mbar_wait(xbar + ((nrounds - 1) & 1), (uint32_t)((nrounds - 1) >> 1) & 1u) && umma_ok;
+  if (nrounds >= 2) umma_ok = mbar_wait(xbar + (nrounds & 1), (uint32_t)((nrounds - 2) >> 1) & 1u) && umma_ok;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
   __syncthreads();            // every warp is done with the tiles and the Z tables
+#if CYTOF_X_TMEM
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
   for (int t = lane; t < pl.total; t += 32) mine[t] = 0.f;
   __syncwarp();
 #pragma unroll
@@ -688,6 +794,34 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       mine[pl.nm + jt] = nm_t;
     }
   }
+#if CYTOF_X_TMEM
+  // accumulator: lane = row (0..47 D_hi markers, 64..111 D_lo markers), column = feature (0..63 hi, 64..127 lo).
+  // Warp w reads lanes 32 (w & 3) .. + 31 and the column half w >> 2; D_lo g_lo is dropped.
+  {
+    const int q = warp & 3, ch = warp >> 2;
+    const int j = 32 * (q & 1) + lane;
+    if (!(q >= 2 && ch == 1)) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t rr[16];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * ch + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
+              "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (j < J && nrounds > 0) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int k = c0 + c;
+            if (k < K) mine[pl.dZ + k * J + j] += __uint_as_float(rr[c]);
+          }
+        }
+      }
+    }
+  }
+#else
   // dZ fragments of n-tile `warp`: (mt, r) -> marker 6g + 2mt + (r >> 1), feature 8 warp + 2 t4 + (r & 1)
 #pragma unroll
   for (int mt = 0; mt < kXMTJ; ++mt)
@@ -696,6 +830,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       const int j = 6 * g + 2 * mt + (r >> 1), k = 8 * warp + 2 * t4 + (r & 1);
       if (j < J && k < K) mine[pl.dZ + k * J + j] = dZ[mt][r];
     }
+#endif
   if (t4 == 0) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -715,6 +850,9 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     double* md = reinterpret_cast<double*>(mine + pl.dbl);
     md[0] = (double)fac * (ll2 * 0.6931471805599453 + (double)lmiss_l);
     md[1] = (double)fac * (double)p.scale * (double)lqy_l;
+#if CYTOF_X_TMEM
+    if (!umma_ok) md[0] = __longlong_as_double(0x7ff8000000000000ll);     // an MMA wait timed out: poison, never hang
+#endif
   }
   __syncthreads();
   float* out = p.partials + (size_t)blockIdx.x * pl.total;
@@ -730,6 +868,11 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     for (int w = 0; w < kXWarps; ++w) a += reinterpret_cast<const double*>(sred + w * pl.total + pl.dbl)[threadIdx.x];
     reinterpret_cast<double*>(out + pl.dbl)[threadIdx.x] = a;
   }
+#if CYTOF_X_TMEM
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem_acc) : "memory");
+#endif
 }
 
 }  // namespace cytof
