@@ -82,6 +82,7 @@ _PROTOS = {
     'cytof_adam_step_f64': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.c_double, C.c_int64, _P, _P, _P]),
     'cytof_sample_minibatch': (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
+    'cytof_sample_minibatch_multi': (C.c_int, [C.c_int32, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P]),
     'cytof_sample_minibatch_dev': (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, _P, C.c_int32, _P, _P]),
 }
 EXPORTS = tuple(_PROTOS)

@@ -89,6 +89,38 @@ __global__ void sample_minibatch_kernel(long long N, long long m, unsigned long 
   } while (x >= (unsigned long long)N);
   out[t] = (int32_t)x;
 }
+// all I samples in ONE launch (blockIdx.y = sample): the CUDA-graph step needs a single sampler node
+struct MultiSample {
+  long long N[CYTOF_MAX_SAMPLES], m[CYTOF_MAX_SAMPLES], off[CYTOF_MAX_SAMPLES];
+  int hbits[CYTOF_MAX_SAMPLES];
+};
+__global__ void sample_minibatch_multi_kernel(const MultiSample ms, unsigned long long seed,
+                                              const long long* __restrict__ step_dev, unsigned long long step_host,
+                                              int32_t* __restrict__ out) {
+  const int i = blockIdx.y;
+  const long long N = ms.N[i], m = ms.m[i];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  int32_t* o = out + ms.off[i];
+  if (m >= N) { o[t] = (int32_t)t; return; }
+  const unsigned long long key = sampler_key(seed, step_dev ? (unsigned long long)(*step_dev + 1) : step_host, i);
+  const int hbits = ms.hbits[i];
+  const uint32_t hmask = (1u << hbits) - 1u;
+  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  unsigned long long x = (unsigned long long)t;
+  do {
+    uint32_t L = (uint32_t)(x >> hbits) & hmask, R = (uint32_t)x & hmask;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r) ^ (k1 << (r & 7))) & hmask;
+      const uint32_t nl = R;
+      R = L ^ f;
+      L = nl;
+    }
+    x = ((unsigned long long)L << hbits) | R;
+  } while (x >= (unsigned long long)N);
+  o[t] = (int32_t)x;
+}
 __global__ void iota_kernel(long long N, int32_t* __restrict__ out) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < N) out[t] = (int32_t)t;
@@ -338,6 +370,30 @@ int cytof_sample_minibatch_dev(int64_t N, int64_t m, uint64_t seed, const int64_
                                int32_t sample, int32_t* idx_out, void* stream) {
   if (!step_dev) return CYTOF_EINVAL;
   return sample_minibatch_impl(N, m, seed, 0, step_dev, sample, idx_out, stream);
+}
+int cytof_sample_minibatch_multi(int32_t I, const int64_t* N, const int64_t* m, uint64_t seed, uint64_t step,
+                                 const int64_t* step_dev, int32_t* idx_out, void* stream) {
+  if (!idx_out || !N || !m || I < 1 || I > CYTOF_MAX_SAMPLES) return CYTOF_EINVAL;
+  MultiSample ms;
+  long long off = 0, mmax = 0;
+  for (int i = 0; i < I; ++i) {
+    if (N[i] < 0 || m[i] < 0 || N[i] > 0x7fffffffLL) return CYTOF_EINVAL;
+    ms.N[i] = N[i];
+    ms.m[i] = m[i] < N[i] ? m[i] : N[i];
+    ms.off[i] = off;
+    off += ms.m[i];
+    int bits = 1;
+    while ((1LL << bits) < N[i]) ++bits;
+    ms.hbits[i] = (bits + 1) / 2 < 1 ? 1 : (bits + 1) / 2;
+    if (ms.m[i] > mmax) mmax = ms.m[i];
+  }
+  if (mmax == 0) return CYTOF_OK;
+  const dim3 grid((unsigned)((mmax + 255) / 256), (unsigned)I);
+  sample_minibatch_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      ms, seed, reinterpret_cast<const long long*>(step_dev), step, idx_out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_cuda_err(err); return CYTOF_ECUDA; }
+  return CYTOF_OK;
 }
 
 }  // extern "C"

@@ -193,17 +193,17 @@ class FusedStep:
         if self.peers is not None:
             assert self.peers.seq == self.t, 'peer sequence and step count must run in lock step'
             self.peers.desc.seq_dev = sd
-        offs = np.concatenate([[0], np.cumsum(counts)])
+        n_arr = (C.c_int64 * I)(*[int(n) for n in eng.N_local])
+        m_arr = (C.c_int64 * I)(*[int(c) for c in counts])
         seed = C.c_uint64(self.g.seed)
 
         def body():
             stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
             with torch.cuda.device(self.dev):
-                if idx_buf is not None:
-                    for i in range(I):
-                        _lib.check(self.lib.cytof_sample_minibatch_dev(
-                            C.c_int64(eng.N_local[i]), C.c_int64(counts[i]), seed, C.c_void_p(sd), C.c_int32(i),
-                            C.c_void_p(idx_buf.data_ptr() + 4 * int(offs[i])), stream))
+                if idx_buf is not None:      # every sample's minibatch in one launch
+                    _lib.check(self.lib.cytof_sample_minibatch_multi(
+                        C.c_int32(I), n_arr, m_arr, seed, C.c_uint64(0), C.c_void_p(sd),
+                        C.c_void_p(idx_buf.data_ptr()), stream))
                 _lib.check(self.lib.cytof_global_fwd_f64(
                     C.byref(g), _ptr(self.theta), _ptr(None), _ptr(self.stash), _ptr(self.globals),
                     _ptr(self.zmask), _ptr(self.scalars_in), stream))
@@ -220,7 +220,7 @@ class FusedStep:
                     _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                     _ptr(self.step_dev), _ptr(self.flag), C.c_int32(1), stream))
 
-        self._graph_launches = 8 + (I if idx_buf is not None else 0)
+        self._graph_launches = 8 + (1 if idx_buf is not None else 0)
         self._graph_idx = idx_buf
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

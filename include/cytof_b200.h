@@ -173,6 +173,11 @@ int cytof_adam_step_f64(double* param, const double* grad, double* exp_avg, doub
  * key = (seed, step, sample)), O(m) work and no scratch.  m >= N writes 0..N-1 (fit.py:98-99). */
 int cytof_sample_minibatch(int64_t N, int64_t m, uint64_t seed, uint64_t step, int32_t sample,
                            int32_t* idx_out, void* stream);
+/* The draws of ALL samples in one launch: sample i gets min(m[i], N[i]) indices (0..N-1 in order when
+ * m[i] >= N[i]) at idx_out + sum_{i' < i} min(m, N); same keyed bijection as cytof_sample_minibatch
+ * (identical indices).  step_dev non-NULL: the step is *step_dev + 1, read on the device. */
+int cytof_sample_minibatch_multi(int32_t I, const int64_t* N, const int64_t* m, uint64_t seed, uint64_t step,
+                                 const int64_t* step_dev, int32_t* idx_out, void* stream);
 /* Same draw with the step read on the device (*step_dev + 1): capturable in a CUDA graph. */
 int cytof_sample_minibatch_dev(int64_t N, int64_t m, uint64_t seed, const int64_t* step_dev,
                                int32_t sample, int32_t* idx_out, void* stream);
