@@ -446,7 +446,10 @@ elbo_fwdbwd_kernel(const ElboParams p) {
 // kFinLanes threads per output of the gradient block (+ ll, log_qy): lane s sums the per-CTA
 // records s, s + kFinLanes, ... of the relevant sample(s) in fp64, the lanes are combined by a
 // fixed butterfly (=> reproducible for a given grid), then the per-sample scalings are applied.
-constexpr int kFinLanes = 8;
+#ifndef CYTOF_FIN_LANES
+#define CYTOF_FIN_LANES 32
+#endif
+constexpr int kFinLanes = CYTOF_FIN_LANES;     // 8, 16 or 32 lanes per output
 
 // One-shot all-reduce over NVLink / NVSwitch peer memory, fused into the finalise kernel.  Every
 // rank owns a mailbox (cudaMalloc'ed by cytof_peer_alloc, mapped into the peers with CUDA IPC):
@@ -486,7 +489,8 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = gt / kFinLanes, sub = gt % kFinLanes;
   const bool live = t < bl.total + 2;      // whole lane groups are live or not together
-  const unsigned gmask = ((1u << kFinLanes) - 1u) << ((threadIdx.x & 31) / kFinLanes * kFinLanes);
+  const unsigned gmask = kFinLanes >= 32 ? 0xffffffffu
+                                         : ((1u << (kFinLanes & 31)) - 1u) << ((threadIdx.x & 31) / kFinLanes * kFinLanes);
   const float* __restrict__ P = p.partials;
   const float* __restrict__ G = p.globals;
   auto group_sum = [&](double a) -> double {
