@@ -333,8 +333,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
-                    help='N>1: one-shot all-reduce over peer memory fused into the finalise kernel, or NCCL')
+    ap.add_argument('--allreduce', default='auto', choices=['auto', 'peer', 'nccl'],
+                    help='N>1: one-shot all-reduce over peer memory fused into the finalise kernel (auto: NCCL if the '
+                         'mailboxes cannot be mapped), or NCCL')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     rank = int(os.environ.get('RANK', 0))

@@ -110,9 +110,14 @@ class FusedStep:
         # kernel; 'nccl' = separate torch.distributed all-reduce (kept for A/B measurements)
         self.graph = None
         self.peers = None
-        if model.dist_group is not None and allreduce == 'peer':
+        if model.dist_group is not None and allreduce in ('peer', 'auto'):
             from .peer import PeerMailboxes
-            self.peers = PeerMailboxes(self.eng, model.dist_group)
+            try:
+                self.peers = PeerMailboxes(self.eng, model.dist_group)
+            except RuntimeError:
+                if allreduce == 'peer':
+                    raise
+                self.peers = None      # 'auto': every rank raised together (peer.py) -> NCCL all-reduce on all ranks
         self._bind()
 
     def _bind(self):

@@ -27,22 +27,38 @@ class PeerMailboxes:
         if nbytes == 0:
             raise RuntimeError('cytofpy_b200: descriptor rejected by cytof_peer_mailbox_bytes')
         self.ptrs = [None] * self.world
-        with torch.cuda.device(self.device):
-            own = C.c_void_p()
-            _lib.check(self.lib.cytof_peer_alloc(C.c_size_t(nbytes), C.byref(own)))
-            handle = C.create_string_buffer(64)
-            _lib.check(self.lib.cytof_ipc_get_handle(own, handle))
-        self.ptrs[self.rank] = own.value
+        # every step below that can fail is followed by an agreement over ALL ranks, so that a rank
+        # that cannot map a peer makes every rank raise instead of leaving the others in a collective
+        err, handle = None, C.create_string_buffer(64)
+        try:
+            with torch.cuda.device(self.device):
+                own = C.c_void_p()
+                _lib.check(self.lib.cytof_peer_alloc(C.c_size_t(nbytes), C.byref(own)))
+                _lib.check(self.lib.cytof_ipc_get_handle(own, handle))
+            self.ptrs[self.rank] = own.value
+        except RuntimeError as e:
+            err = str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        with torch.cuda.device(self.device):
-            for q in range(self.world):
-                if q == self.rank:
-                    continue
-                ptr = C.c_void_p()
-                _lib.check(self.lib.cytof_ipc_open_handle(C.c_char_p(handles[q]), C.byref(ptr)))
-                self.ptrs[q] = ptr.value
-        dist.barrier(group=group)       # every mailbox is mapped everywhere before the first step
+        dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
+        if err is None and any(h is None for h in handles):
+            err = 'a peer could not allocate / export its mailbox'
+        if err is None:
+            try:
+                with torch.cuda.device(self.device):
+                    for q in range(self.world):
+                        if q == self.rank:
+                            continue
+                        ptr = C.c_void_p()
+                        _lib.check(self.lib.cytof_ipc_open_handle(C.c_char_p(handles[q]), C.byref(ptr)))
+                        self.ptrs[q] = ptr.value
+            except RuntimeError as e:
+                err = str(e)
+        status = [None] * self.world
+        dist.all_gather_object(status, err, group=group)    # also the barrier: every mailbox is mapped everywhere
+        if any(st is not None for st in status):
+            self.close()
+            raise RuntimeError('cytofpy_b200: peer-memory mailboxes unavailable (%s); use allreduce="nccl"'
+                               % next(st for st in status if st is not None))
         self.seq = 0
         self.desc = _lib.PeerDesc()
         self.desc.world, self.desc.rank = self.world, self.rank

@@ -191,3 +191,31 @@ def test_cuda_graph_step_equals_host_driven_steps(mb, nan_rate):
     s = ref.t + 1
     idx = [range(n) for n in ref_mod.N_local] if mb is None else device_minibatch(ref_mod, mb, s, ref.g.seed)
     assert a == ref.step(idx).tolist()
+
+
+def test_multi_sample_sampler_equals_per_sample_calls():
+    """cytof_sample_minibatch_multi (one launch for all samples, host step or device step counter)
+    draws exactly the indices of the per-sample cytof_sample_minibatch calls."""
+    dev = torch.device('cuda', 0)
+    lib = _lib.load()
+    N, m = [40000, 41474, 17, 500], [2000, 500, 16, 800]      # last sample: m >= N -> 0..N-1 in order
+    I = len(N)
+    seed, step = 12345, 7
+    take = [min(a, b) for a, b in zip(m, N)]
+    ref = torch.empty(sum(take), dtype=torch.int32, device=dev)
+    off = 0
+    for i in range(I):
+        _lib.check(lib.cytof_sample_minibatch(N[i], m[i], seed, step, i, C.c_void_p(ref.data_ptr() + 4 * off),
+                                              C.c_void_p(0)))
+        off += take[i]
+    n_arr, m_arr = (C.c_int64 * I)(*N), (C.c_int64 * I)(*m)
+    out = torch.full_like(ref, -1)
+    _lib.check(lib.cytof_sample_minibatch_multi(I, n_arr, m_arr, seed, step, C.c_void_p(0), _p(out), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    step_dev = torch.tensor([step - 1], dtype=torch.int64, device=dev)      # device counter: step = *step_dev + 1
+    out2 = torch.full_like(ref, -1)
+    _lib.check(lib.cytof_sample_minibatch_multi(I, n_arr, m_arr, seed, 0, _p(step_dev), _p(out2), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref)
+    assert torch.equal(out[-500:].cpu(), torch.arange(500, dtype=torch.int32))
