@@ -7,7 +7,7 @@
 A "step" is one full `update` of the reference (fit.py:32-48): draw the global
 sample, transforms, per-cell ELBO forward+backward over ONE batch (the fused
 CUDA kernel), log prior, entropy, backward to every variational parameter, NaN
-scrub and the Adam step — here 8 kernel launches (cytofpy_b200/model/fused.py).  The default workload is BASELINE.json configs[3]
+scrub and the Adam step — here 5 kernel launches (cytofpy_b200/model/fused.py).  The default workload is BASELINE.json configs[3]
 ("cfg4": full batch, I=8, J=32, K=30, L=5/5) — the configuration the metric
 string names — with 1,000,000 cells PER GPU (weak scaling: rank r holds rows
 [r*125000, (r+1)*125000) of each of the 8 samples; one all-reduce of the

@@ -95,10 +95,34 @@ __device__ __forceinline__ RowPos row_pos(const GlobalParams& p, int b, int loca
 constexpr int kElemCtas = 24;
 constexpr int kElemThreads = 256;
 
+__device__ __forceinline__ void
+global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* aux2, float* __restrict__ globals,
+                     unsigned long long* __restrict__ zmask, const double* cta_part, double* __restrict__ scalars,
+                     const int staged, double* dyn);
+__device__ __forceinline__ void
+global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, const double* aux1, const double* aux2,
+                     const double* packed, double* __restrict__ greal, const int staged, double* dyn);
+
+// true in exactly one CTA of the grid: the one that finishes last (its threads then see everything the
+// other CTAs wrote before their ticket); the ticket is left at 0 for the next launch
+__device__ __forceinline__ bool last_cta_done(unsigned* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
+  __syncthreads();
+  if (!s_last) return false;
+  if (threadIdx.x == 0) *ticket = 0u;
+  __threadfence();
+  return true;
+}
+
 __global__ void __launch_bounds__(kElemThreads)
 global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, const double* __restrict__ eps_in,
                        double* __restrict__ real, double* __restrict__ eps_out, double* __restrict__ aux1,
-                       double* __restrict__ aux2, float* __restrict__ globals, double* __restrict__ cta_part) {
+                       double* __restrict__ aux2, float* __restrict__ globals, double* __restrict__ cta_part,
+                       unsigned* ticket, unsigned long long* zmask, double* scalars) {
+  extern __shared__ double dyn[];
   __shared__ double sh[32];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -174,19 +198,33 @@ global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, c
   lp = block_sum(lp, sh);
   lq = block_sum(lq, sh);
   if (threadIdx.x == 0) { cta_part[2 * blockIdx.x] = lp; cta_part[2 * blockIdx.x + 1] = lq; }
+  // fused tail: the last CTA to finish runs the scans (ticket == NULL: separate global_fwd_scan_kernel)
+  if (ticket && last_cta_done(ticket)) global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, 1, dyn);
 }
 
-// (2) one CTA: serial scans (adds / multiplies only), Z bit mask, final lp / lq
-__global__ void __launch_bounds__(1024, 1)
-global_fwd_scan_kernel(const GlobalParams p, const double* __restrict__ aux1, const double* __restrict__ aux2,
-                       float* __restrict__ globals, unsigned long long* __restrict__ zmask,
-                       const double* __restrict__ cta_part, double* __restrict__ scalars /* lp, lq_global */) {
+// (2) one CTA: serial scans (adds / multiplies only), Z bit mask, final lp / lq.  Runs either as its
+// own kernel or -- the normal case -- as the tail of the LAST CTA of the element kernel (one launch
+// less per step; the inputs are then always staged through shared memory with L2-coherent loads).
+__device__ __forceinline__ void
+global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* aux2,
+                     float* __restrict__ globals, unsigned long long* __restrict__ zmask,
+                     const double* cta_part, double* __restrict__ scalars /* lp, lq_global */,
+                     const int staged, double* dyn) {
   __shared__ double sh[32];
   __shared__ double s_vc[CYTOF_MAX_K];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
   double lp = 0.0;
+  // the scans below are serial chains of loads: from global memory every step costs an L2 round trip
+  // (the kernel took 10 us for 1.7 k values); stage aux1 / aux2 in shared memory with all threads first
+  if (staged) {
+    const int R = p.roff[B_COUNT];
+    for (int q = tid; q < R; q += nt) { dyn[q] = __ldcg(aux1 + q); dyn[R + q] = __ldcg(aux2 + q); }
+    __syncthreads();
+    aux1 = dyn;
+    aux2 = dyn + R;
+  }
 
   if (tid == 0) {   // mu0 = -cumsum(delta0)   (Model.py:223)
     double c = 0.0;
@@ -239,10 +277,18 @@ global_fwd_scan_kernel(const GlobalParams p, const double* __restrict__ aux1, co
   lp = block_sum(lp, sh);
   if (tid == 0) {
     double lq = 0.0;
-    for (int c = 0; c < kElemCtas; ++c) { lp += cta_part[2 * c]; lq += cta_part[2 * c + 1]; }   // fixed order
+    for (int c = 0; c < kElemCtas; ++c) { lp += __ldcg(cta_part + 2 * c); lq += __ldcg(cta_part + 2 * c + 1); }   // fixed order
     scalars[0] = lp;
     scalars[1] = lq;
   }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+global_fwd_scan_kernel(const GlobalParams p, const double* aux1, const double* aux2, float* __restrict__ globals,
+                       unsigned long long* __restrict__ zmask, const double* cta_part, double* __restrict__ scalars,
+                       const int staged) {
+  extern __shared__ double dyn[];
+  global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, staged, dyn);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,7 +297,8 @@ global_fwd_scan_kernel(const GlobalParams p, const double* __restrict__ aux1, co
 __global__ void __launch_bounds__(kElemThreads)
 global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
                        double* __restrict__ aux2, const double* __restrict__ packed, double* __restrict__ greal,
-                       int* __restrict__ flag) {
+                       int* __restrict__ flag, unsigned* ticket) {
+  extern __shared__ double dyn[];
   __shared__ double s_vc[CYTOF_MAX_K], s_lvc[CYTOF_MAX_K];
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
@@ -301,18 +348,28 @@ global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, co
       default: break;                    // delta0 / delta1 / alpha / v: scan kernel
     }
   }
+  if (ticket && last_cta_done(ticket)) global_bwd_scan_body(p, real, aux1, aux2, packed, greal, 1, dyn);
 }
 
 // (2) one CTA: suffix scans (cumsum / cumprod / stick-breaking backward), adds and multiplies only
-__global__ void __launch_bounds__(1024, 1)
-global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
-                       const double* __restrict__ aux2, const double* __restrict__ packed,
-                       double* __restrict__ greal) {
+__device__ __forceinline__ void
+global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, const double* aux1,
+                     const double* aux2, const double* packed,
+                     double* __restrict__ greal, const int staged, double* dyn) {
   __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
-  const double* __restrict__ G = packed;
+  if (staged) {      // serial suffix scans: stage aux1 / aux2 / the gradient block in shared memory (see fwd scan)
+    const int R = p.roff[B_COUNT], NB = bl.total + 2;
+    for (int q = tid; q < R; q += nt) { dyn[q] = __ldcg(aux1 + q); dyn[R + q] = __ldcg(aux2 + q); }
+    for (int q = tid; q < NB; q += nt) dyn[2 * R + q] = __ldcg(packed + q);
+    __syncthreads();
+    aux1 = dyn;
+    aux2 = dyn + R;
+    packed = dyn + 2 * R;
+  }
+  const double* G = packed;
   if (tid == 96) {
     double cp = 1.0;
     for (int k = 0; k < K; ++k) { cp = p.use_stick_break ? cp * aux1[p.roff[B_V] + k] : aux1[p.roff[B_V] + k]; s_vc[k] = cp; }
@@ -376,13 +433,20 @@ global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, co
   }
 }
 
+__global__ void __launch_bounds__(1024, 1)
+global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, const double* aux1, const double* aux2,
+                       const double* packed, double* __restrict__ greal, const int staged) {
+  extern __shared__ double dyn[];
+  global_bwd_scan_body(p, real, aux1, aux2, packed, greal, staged, dyn);
+}
+
 // (3) element-parallel: chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
 __global__ void __launch_bounds__(kElemThreads)
 global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const double* __restrict__ eps,
                    const double* __restrict__ packed, const double* __restrict__ scalars_in,
                    const double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
                    double* __restrict__ grad_out, double* __restrict__ out_scalars,
-                   const long long* __restrict__ step_dev, int* __restrict__ flag, int do_update) {
+                   long long* step_dev, int* flag, int do_update, unsigned* ticket) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
@@ -425,14 +489,13 @@ global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const doubl
     out_scalars[2] = lp;
     out_scalars[3] = lq;
   }
+  // after ALL CTAs: out_scalars[4] = 1 if any NaN gradient was scrubbed in this step; bump the device step
+  // counter (every CTA read it at its start)
+  if (last_cta_done(ticket) && threadIdx.x == 0) {
+    out_scalars[4] = flag ? (double)*reinterpret_cast<volatile int*>(flag) : 0.0;
+    if (step_dev && do_update) *step_dev += 1;
+  }
 }
-
-// out_scalars[4] = 1 if any NaN gradient was scrubbed in this step (after all CTAs of the Adam kernel)
-__global__ void finish_step_kernel(long long* step_dev, const int* flag, double* out_scalars, int bump) {
-  out_scalars[4] = flag ? (double)*flag : 0.0;
-  if (step_dev && bump) *step_dev += 1;
-}
-
 
 // ---------------------------------------------------------------------------------------------
 static void fill_layout(GlobalParams* p) {
@@ -496,8 +559,25 @@ int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
   out[0] = p.roff[B_COUNT];                 // R: number of global reals (= noise length)
   out[1] = p.n_global;                      // 2R: scrubbed prefix of theta
   out[2] = p.n_global + 2 * p.I * p.J;      // P: length of theta
-  out[3] = 5 * (int64_t)p.roff[B_COUNT] + 2 * kElemCtas;   // stash: real | eps | greal | aux1 | aux2 | CTA partials
+  out[3] = 5 * (int64_t)p.roff[B_COUNT] + 2 * kElemCtas + 2;   // stash: real | eps | greal | aux1 | aux2 | CTA partials | 3 tickets
   return CYTOF_OK;
+}
+
+// dynamic shared memory for the staged scans: `want` bytes if they fit (opt-in above 48 KB, once per
+// device and kernel), else 0 = separate scan kernels reading global memory
+static size_t scan_smem_bytes(const void* fn, int which, size_t want) {
+  static size_t granted[64][4] = {};
+  if (want > 200 * 1024) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return want <= 48 * 1024 ? want : 0;
+  if (want > 48 * 1024 && want > granted[dev][which]) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+    granted[dev][which] = want;
+  }
+  return want;
 }
 
 int launch_global_fwd(const cytof_global_desc* g, const double* theta, const double* eps_in, double* stash,
@@ -506,14 +586,21 @@ int launch_global_fwd(const cytof_global_desc* g, const double* theta, const dou
   const int rc = global_make_params(g, &p);
   if (rc != CYTOF_OK) return rc;
   const int R = p.roff[B_COUNT];
-  global_fwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
-                                                            stash + 4 * R, globals, stash + 5 * R);
-  global_fwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash + 3 * R, stash + 4 * R, globals,
-                                            reinterpret_cast<unsigned long long*>(zmask), stash + 5 * R, scalars);
+  unsigned* tickets = reinterpret_cast<unsigned*>(stash + 5 * (size_t)R + 2 * kElemCtas);
+  unsigned long long* zm = reinterpret_cast<unsigned long long*>(zmask);
+  const size_t want = sizeof(double) * 2 * (size_t)R;
+  const size_t fused = scan_smem_bytes((const void*)global_fwd_elem_kernel, 0, want);
+  if (fused) {      // one launch: the last CTA of the element kernel runs the scans out of shared memory
+    global_fwd_elem_kernel<<<kElemCtas, kElemThreads, fused, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
+                                                                  stash + 4 * R, globals, stash + 5 * R, tickets, zm, scalars);
+  } else {
+    global_fwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
+                                                              stash + 4 * R, globals, stash + 5 * R, nullptr, zm, scalars);
+    global_fwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash + 3 * R, stash + 4 * R, globals, zm, stash + 5 * R, scalars, 0);
+  }
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
-
 int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, const double* packed,
                       const double* scalars_in, double* adam_m, double* adam_v, double* grad_out,
                       double* out_scalars, int64_t* step_dev, int32_t* flag, int do_update, cudaStream_t s,
@@ -522,13 +609,21 @@ int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, 
   const int rc = global_make_params(g, &p);
   if (rc != CYTOF_OK) return rc;
   const int R = p.roff[B_COUNT];
-  global_bwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
-                                                            stash + 2 * R, flag);
-  global_bwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed, stash + 2 * R);
+  unsigned* tickets = reinterpret_cast<unsigned*>(stash + 5 * (size_t)R + 2 * kElemCtas);
+  const BlockLayout blh = block_layout(p.I, p.J, p.K, p.L0, p.L1);
+  const size_t want = sizeof(double) * (2 * (size_t)R + (size_t)blh.total + 2);
+  const size_t fused = scan_smem_bytes((const void*)global_bwd_elem_kernel, 1, want);
+  if (fused) {
+    global_bwd_elem_kernel<<<kElemCtas, kElemThreads, fused, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
+                                                                  stash + 2 * R, flag, tickets + 1);
+  } else {
+    global_bwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
+                                                              stash + 2 * R, flag, nullptr);
+    global_bwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed, stash + 2 * R, 0);
+  }
   global_adam_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
                                                         adam_v, grad_out, out_scalars,
-                                                        reinterpret_cast<const long long*>(step_dev), flag, do_update);
-  finish_step_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_dev), flag, out_scalars, do_update);
+                                                        reinterpret_cast<long long*>(step_dev), flag, do_update, tickets + 2);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }

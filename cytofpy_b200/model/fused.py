@@ -1,4 +1,4 @@
-"""The whole ADVI step as five kernel launches behind the C ABI:
+"""The whole ADVI step as five kernel launches behind the C ABI (global fwd 1, per-cell 2, global bwd 1, Adam 1):
 
     [cytof_sample_minibatch x I]  ->  cytof_global_fwd_f64  ->  cytof_elbo_fwdbwd_packed (2 kernels)
         ->  [NCCL all-reduce of the packed gradient block when cells are sharded]
@@ -97,6 +97,11 @@ class FusedStep:
         self.theta, self.adam_m, self.adam_v, self.grad = z(self.P), z(self.P), z(self.P), z(self.P)
         self.stash = z(stash_len)
         self.packed = z(self.eng.b_off[-1] + 2)
+        # launches of the global part (csrc/global_part.cu): the scans run in the last CTA of the element
+        # kernels when their operands fit in shared memory (200 KB), else as kernels of their own
+        smem = 200 * 1024
+        self._global_launches = ((1 if 16 * self.R <= smem else 2) +
+                                 (2 if 8 * (2 * self.R + self.packed.numel()) <= smem else 3))
         self.scalars_in, self.scalars = z(2), z(5)
         self.globals = z(self.eng.g_off[-1], torch.float32)
         o = self.eng.g_off
@@ -170,7 +175,7 @@ class FusedStep:
                 C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
                 _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
-        self.launches += 8      # global fwd (2) + per-cell (2) + global bwd / Adam (4)
+        self.launches += 2 + self._global_launches      # per-cell (2) + global fwd, bwd, Adam
         return self.scalars
 
     # ------------------------------------------------------------------ CUDA graph
@@ -225,7 +230,7 @@ class FusedStep:
                     _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                     _ptr(self.step_dev), _ptr(self.flag), C.c_int32(1), stream))
 
-        self._graph_launches = 8 + (1 if idx_buf is not None else 0)
+        self._graph_launches = 2 + self._global_launches + (1 if idx_buf is not None else 0)
         self._graph_idx = idx_buf
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -296,5 +301,5 @@ class FusedStep:
                 C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
                 _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
-        self.launches += 2 + 2 * I + 4
+        self.launches += 2 * I + self._global_launches
         return self.scalars
