@@ -98,10 +98,11 @@ constexpr int kElemThreads = 256;
 __device__ __forceinline__ void
 global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* aux2, float* __restrict__ globals,
                      unsigned long long* __restrict__ zmask, const double* cta_part, double* __restrict__ scalars,
-                     const int staged, double* dyn);
+                     double* extra, const int staged, double* dyn);
 __device__ __forceinline__ void
 global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, const double* aux1, const double* aux2,
-                     const double* packed, double* __restrict__ greal, const int staged, double* dyn);
+                     const double* packed, double* __restrict__ greal, double* extra, const long long* adam_step_dev,
+                     const int staged, double* dyn);
 
 // true in exactly one CTA of the grid: the one that finishes last (its threads then see everything the
 // other CTAs wrote before their ticket); the ticket is left at 0 for the next launch
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kElemThreads)
 global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, const double* __restrict__ eps_in,
                        double* __restrict__ real, double* __restrict__ eps_out, double* __restrict__ aux1,
                        double* __restrict__ aux2, float* __restrict__ globals, double* __restrict__ cta_part,
-                       unsigned* ticket, unsigned long long* zmask, double* scalars) {
+                       unsigned* ticket, unsigned long long* zmask, double* scalars, double* extra) {
   extern __shared__ double dyn[];
   __shared__ double sh[32];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
@@ -199,7 +200,7 @@ global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, c
   lq = block_sum(lq, sh);
   if (threadIdx.x == 0) { cta_part[2 * blockIdx.x] = lp; cta_part[2 * blockIdx.x + 1] = lq; }
   // fused tail: the last CTA to finish runs the scans (ticket == NULL: separate global_fwd_scan_kernel)
-  if (ticket && last_cta_done(ticket)) global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, 1, dyn);
+  if (ticket && last_cta_done(ticket)) global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, extra, 1, dyn);
 }
 
 // (2) one CTA: serial scans (adds / multiplies only), Z bit mask, final lp / lq.  Runs either as its
@@ -209,6 +210,7 @@ __device__ __forceinline__ void
 global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* aux2,
                      float* __restrict__ globals, unsigned long long* __restrict__ zmask,
                      const double* cta_part, double* __restrict__ scalars /* lp, lq_global */,
+                     double* extra /* out: cumprod(v)[MAX_K] | logit of it [MAX_K] for the backward pass */,
                      const int staged, double* dyn) {
   __shared__ double sh[32];
   __shared__ double s_vc[CYTOF_MAX_K];
@@ -268,6 +270,10 @@ global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* au
     }
   }
   __syncthreads();
+  for (int k = nt - 1 - tid; k >= 0 && k < K; k += nt) {     // for the backward pass (the last threads: the first hold Z rows)
+    extra[k] = s_vc[k];
+    extra[CYTOF_MAX_K + k] = log(s_vc[k]) - log1p(-s_vc[k]);
+  }
   for (int j = tid; j < J; j += nt) {       // Z = 1[v > H], thresholded in fp64 (Model.py:33)
     unsigned long long m = 0ull;
     for (int k = 0; k < K; ++k)
@@ -286,9 +292,9 @@ global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* au
 __global__ void __launch_bounds__(1024, 1)
 global_fwd_scan_kernel(const GlobalParams p, const double* aux1, const double* aux2, float* __restrict__ globals,
                        unsigned long long* __restrict__ zmask, const double* cta_part, double* __restrict__ scalars,
-                       const int staged) {
+                       double* extra, const int staged) {
   extern __shared__ double dyn[];
-  global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, staged, dyn);
+  global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, extra, staged, dyn);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -297,22 +303,17 @@ global_fwd_scan_kernel(const GlobalParams p, const double* aux1, const double* a
 __global__ void __launch_bounds__(kElemThreads)
 global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
                        double* __restrict__ aux2, const double* __restrict__ packed, double* __restrict__ greal,
-                       int* __restrict__ flag, unsigned* ticket) {
+                       int* __restrict__ flag, unsigned* ticket, double* extra, const long long* adam_step_dev) {
   extern __shared__ double dyn[];
-  __shared__ double s_vc[CYTOF_MAX_K], s_lvc[CYTOF_MAX_K];
+  __shared__ double s_lvc[CYTOF_MAX_K];
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const double* __restrict__ G = packed;
   if (flag && blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
 
-  // ---- (0) cumprod(v) and logit of it (K values; every CTA recomputes its own copy)
-  if (threadIdx.x == 0) {
-    double cp = 1.0;
-    for (int k = 0; k < K; ++k) { cp = p.use_stick_break ? cp * aux1[p.roff[B_V] + k] : aux1[p.roff[B_V] + k]; s_vc[k] = cp; }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) s_lvc[k] = log(s_vc[k]) - log1p(-s_vc[k]);
+  // ---- (0) logit of cumprod(v): left in the stash by the forward scan
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_lvc[k] = extra[CYTOF_MAX_K + k];
   __syncthreads();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   (void)I; (void)J; (void)L0; (void)L1;
@@ -348,15 +349,16 @@ global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, co
       default: break;                    // delta0 / delta1 / alpha / v: scan kernel
     }
   }
-  if (ticket && last_cta_done(ticket)) global_bwd_scan_body(p, real, aux1, aux2, packed, greal, 1, dyn);
+  if (ticket && last_cta_done(ticket)) global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, 1, dyn);
 }
 
 // (2) one CTA: suffix scans (cumsum / cumprod / stick-breaking backward), adds and multiplies only
 __device__ __forceinline__ void
 global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, const double* aux1,
                      const double* aux2, const double* packed,
-                     double* __restrict__ greal, const int staged, double* dyn) {
-  __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K];
+                     double* __restrict__ greal, double* extra, const long long* adam_step_dev, const int staged,
+                     double* dyn) {
+  __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K], s_suf[CYTOF_MAX_K], s_red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
@@ -370,11 +372,13 @@ global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, con
     packed = dyn + 2 * R;
   }
   const double* G = packed;
-  if (tid == 96) {
-    double cp = 1.0;
-    for (int k = 0; k < K; ++k) { cp = p.use_stick_break ? cp * aux1[p.roff[B_V] + k] : aux1[p.roff[B_V] + k]; s_vc[k] = cp; }
-  }
+  for (int k = tid; k < K; k += nt) s_vc[k] = extra[k];      // cumprod(v) from the forward scan
   __syncthreads();
+  if (tid == 96) {   // Adam bias corrections of this step for global_adam_kernel (two pow() off its critical path)
+    const long long step = adam_step_dev ? (*adam_step_dev + 1) : p.step_host;
+    extra[2 * CYTOF_MAX_K] = 1.0 - pow(p.beta1, (double)step);
+    extra[2 * CYTOF_MAX_K + 1] = sqrt(1.0 - pow(p.beta2, (double)step));
+  }
 
   if (tid == 0) {
     double suf = 0.0;
@@ -416,28 +420,37 @@ global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, con
     }
   }
   __syncthreads();
-  if (tid == 0) {   // cumprod backward, v prior Beta(conc, 1), alpha
-    const double ra = real[p.roff[B_ALPHA]], alpha = aux1[p.roff[B_ALPHA]];
-    const double conc = p.use_stick_break ? alpha : alpha / (double)K;
-    double suf = 0.0, dconc = 0.0;
-    for (int m = K - 1; m >= 0; --m) {
-      const double v = aux1[p.roff[B_V] + m];
-      double gv;
-      if (p.use_stick_break) { suf += s_gvc[m] * s_vc[m]; gv = suf / v; } else { gv = s_gvc[m]; }
-      greal[p.roff[B_V] + m] = v * (1.0 - v) * (gv + (conc - 1.0) / v) + (1.0 - 2.0 * v);
-      dconc += aux2[p.roff[B_V] + m] + 1.0 / conc;
-    }
+  // cumprod backward, v prior Beta(conc, 1), alpha: the suffix sum is the only serial part (adds only)
+  if (tid == 0) {
+    double suf = 0.0;
+    for (int m = K - 1; m >= 0; --m) { suf += s_gvc[m] * s_vc[m]; s_suf[m] = suf; }
+  }
+  if (tid == 32) {
+    double slv = 0.0;
+    for (int m = K - 1; m >= 0; --m) slv += aux2[p.roff[B_V] + m];      // same order as the serial form
+    s_red[0] = slv;
+  }
+  __syncthreads();
+  const double alpha = aux1[p.roff[B_ALPHA]];
+  const double conc = p.use_stick_break ? alpha : alpha / (double)K;
+  for (int m = tid; m < K; m += nt) {
+    const double v = aux1[p.roff[B_V] + m];
+    const double gv = p.use_stick_break ? s_suf[m] / v : s_gvc[m];
+    greal[p.roff[B_V] + m] = v * (1.0 - v) * (gv + (conc - 1.0) / v) + (1.0 - 2.0 * v);
+  }
+  if (tid == 64) {
+    const double dconc = s_red[0] + (double)K / conc;
     const double dalpha = p.use_stick_break ? dconc : dconc / (double)K;
     greal[p.roff[B_ALPHA]] = alpha * dalpha + (p.alpha_a - 1.0) - p.alpha_b * alpha + 1.0;
-    (void)ra;
   }
 }
 
 __global__ void __launch_bounds__(1024, 1)
 global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, const double* aux1, const double* aux2,
-                       const double* packed, double* __restrict__ greal, const int staged) {
+                       const double* packed, double* __restrict__ greal, double* extra, const long long* adam_step_dev,
+                       const int staged) {
   extern __shared__ double dyn[];
-  global_bwd_scan_body(p, real, aux1, aux2, packed, greal, staged, dyn);
+  global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, staged, dyn);
 }
 
 // (3) element-parallel: chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
@@ -446,14 +459,13 @@ global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const doubl
                    const double* __restrict__ packed, const double* __restrict__ scalars_in,
                    const double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
                    double* __restrict__ grad_out, double* __restrict__ out_scalars,
-                   long long* step_dev, int* flag, int do_update, unsigned* ticket) {
+                   long long* step_dev, int* flag, int do_update, unsigned* ticket, const double* extra) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const double* __restrict__ G = packed;
-  const long long step = step_dev ? (*step_dev + 1) : p.step_host;
-  const double bc1 = 1.0 - pow(p.beta1, (double)step), bc2s = sqrt(1.0 - pow(p.beta2, (double)step));
+  const double bc1 = extra[2 * CYTOF_MAX_K], bc2s = extra[2 * CYTOF_MAX_K + 1];   // from the backward scan
   auto adam = [&](int t, double g, bool scrub) {
     g *= p.grad_scale;
     if (scrub && g != g) { g = 0.0; if (flag) *flag = 1; }
@@ -559,7 +571,8 @@ int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
   out[0] = p.roff[B_COUNT];                 // R: number of global reals (= noise length)
   out[1] = p.n_global;                      // 2R: scrubbed prefix of theta
   out[2] = p.n_global + 2 * p.I * p.J;      // P: length of theta
-  out[3] = 5 * (int64_t)p.roff[B_COUNT] + 2 * kElemCtas + 2;   // stash: real | eps | greal | aux1 | aux2 | CTA partials | 3 tickets
+  // stash: real | eps | greal | aux1 | aux2 | CTA partials | 3 tickets | cumprod(v) | its logit | Adam bias corrections
+  out[3] = 5 * (int64_t)p.roff[B_COUNT] + 2 * kElemCtas + 2 + 2 * CYTOF_MAX_K + 2;
   return CYTOF_OK;
 }
 
@@ -588,15 +601,16 @@ int launch_global_fwd(const cytof_global_desc* g, const double* theta, const dou
   const int R = p.roff[B_COUNT];
   unsigned* tickets = reinterpret_cast<unsigned*>(stash + 5 * (size_t)R + 2 * kElemCtas);
   unsigned long long* zm = reinterpret_cast<unsigned long long*>(zmask);
+  double* extra = stash + 5 * (size_t)R + 2 * kElemCtas + 2;
   const size_t want = sizeof(double) * 2 * (size_t)R;
   const size_t fused = scan_smem_bytes((const void*)global_fwd_elem_kernel, 0, want);
   if (fused) {      // one launch: the last CTA of the element kernel runs the scans out of shared memory
     global_fwd_elem_kernel<<<kElemCtas, kElemThreads, fused, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
-                                                                  stash + 4 * R, globals, stash + 5 * R, tickets, zm, scalars);
+                                                                  stash + 4 * R, globals, stash + 5 * R, tickets, zm, scalars, extra);
   } else {
     global_fwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
-                                                              stash + 4 * R, globals, stash + 5 * R, nullptr, zm, scalars);
-    global_fwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash + 3 * R, stash + 4 * R, globals, zm, stash + 5 * R, scalars, 0);
+                                                              stash + 4 * R, globals, stash + 5 * R, nullptr, zm, scalars, extra);
+    global_fwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash + 3 * R, stash + 4 * R, globals, zm, stash + 5 * R, scalars, extra, 0);
   }
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
@@ -611,19 +625,21 @@ int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, 
   const int R = p.roff[B_COUNT];
   unsigned* tickets = reinterpret_cast<unsigned*>(stash + 5 * (size_t)R + 2 * kElemCtas);
   const BlockLayout blh = block_layout(p.I, p.J, p.K, p.L0, p.L1);
+  double* extra = stash + 5 * (size_t)R + 2 * kElemCtas + 2;
+  const long long* sd = reinterpret_cast<const long long*>(step_dev);
   const size_t want = sizeof(double) * (2 * (size_t)R + (size_t)blh.total + 2);
   const size_t fused = scan_smem_bytes((const void*)global_bwd_elem_kernel, 1, want);
   if (fused) {
     global_bwd_elem_kernel<<<kElemCtas, kElemThreads, fused, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
-                                                                  stash + 2 * R, flag, tickets + 1);
+                                                                  stash + 2 * R, flag, tickets + 1, extra, sd);
   } else {
     global_bwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
-                                                              stash + 2 * R, flag, nullptr);
-    global_bwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed, stash + 2 * R, 0);
+                                                              stash + 2 * R, flag, nullptr, extra, sd);
+    global_bwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed, stash + 2 * R, extra, sd, 0);
   }
   global_adam_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
                                                         adam_v, grad_out, out_scalars,
-                                                        reinterpret_cast<long long*>(step_dev), flag, do_update, tickets + 2);
+                                                        reinterpret_cast<long long*>(step_dev), flag, do_update, tickets + 2, extra);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
