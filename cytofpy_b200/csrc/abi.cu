@@ -70,6 +70,7 @@ __host__ __device__ inline unsigned long long sampler_key(unsigned long long see
 __global__ void sample_minibatch_kernel(long long N, long long m, unsigned long long key, int hbits,
                                         int32_t* __restrict__ out, unsigned long long seed,
                                         const long long* __restrict__ step_dev, int sample) {
+  pdl_enter();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   if (step_dev) key = sampler_key(seed, (unsigned long long)(*step_dev + 1), sample);
@@ -97,6 +98,7 @@ struct MultiSample {
 __global__ void sample_minibatch_multi_kernel(const MultiSample ms, unsigned long long seed,
                                               const long long* __restrict__ step_dev, unsigned long long step_host,
                                               int32_t* __restrict__ out) {
+  pdl_enter();
   const int i = blockIdx.y;
   const long long N = ms.N[i], m = ms.m[i];
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,9 +391,8 @@ int cytof_sample_minibatch_multi(int32_t I, const int64_t* N, const int64_t* m, 
   }
   if (mmax == 0) return CYTOF_OK;
   const dim3 grid((unsigned)((mmax + 255) / 256), (unsigned)I);
-  sample_minibatch_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      ms, seed, reinterpret_cast<const long long*>(step_dev), step, idx_out);
-  cudaError_t err = cudaGetLastError();
+  cudaError_t err = launch_pdl(sample_minibatch_multi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, ms, seed,
+                               reinterpret_cast<const long long*>(step_dev), step, idx_out);
   if (err != cudaSuccess) { set_cuda_err(err); return CYTOF_ECUDA; }
   return CYTOF_OK;
 }

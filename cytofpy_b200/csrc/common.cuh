@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/cytof_b200.h"
 
@@ -210,6 +212,39 @@ KernelFn mma64_kernel_fn(int lidx, int missing, int fi);
 
 __device__ __forceinline__ uint32_t elbo_step(const ElboParams& p) {
   return p.step_dev ? (uint32_t)(*p.step_dev + 1) : p.step;
+}
+
+// ---- programmatic dependent launch (sm_90+): every kernel of the step is launched with the
+// programmatic-stream-serialisation attribute, so its launch and scheduling overlap the drain of the
+// kernel before it; each kernel starts with pdl_enter(), which (1) lets ITS successor start launching
+// and (2) blocks until the predecessor grid has completed and its writes are visible.  Because every
+// kernel in the chain waits before touching memory, completion is transitive.  MEASURED (B200, whole step as
+// one CUDA graph, L2 flushed between steps): cfg2 68.7 us with it vs 57.5 us without, cfg4 0.325 vs 0.304 ms
+// -- graph kernel->kernel edges are already cheap and the early-resident dependents get in the way -- so it
+// is OFF unless CYTOF_PDL=1 is set in the environment (plain stream order; pdl_enter() is then a no-op).
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CYTOF_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
 }
 
 }  // namespace cytof

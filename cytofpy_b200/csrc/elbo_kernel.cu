@@ -40,6 +40,7 @@ namespace cytof {
 template <int LM0, int LM1, int JP, int KP, bool NOISY>
 __global__ void __launch_bounds__(kThreads, (JP == 1 && KP == 1) ? CYTOF_MINBLOCKS : 1)
 elbo_fwdbwd_kernel(const ElboParams p) {
+  pdl_enter();
   constexpr bool ZF = (JP == 1 && KP == 1) && CYTOF_ZFLOAT;  // Z rows/columns as float registers
   constexpr int JW = JP * 32, KW = KP * 32;
   constexpr unsigned FULL = 0xffffffffu;
@@ -482,6 +483,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
                                      double* __restrict__ ll_lqy, double* __restrict__ packed,
                                      const PeerArgs peer) {
+  pdl_enter();
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const PartialLayout pl = partial_layout(J, K, L0, L1);
@@ -866,8 +868,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
   if (nblocks > 0) {
     KernelFn fn = v->fn[fi];
-    fn<<<nblocks, variant_threads(v), smem, stream>>>(p);
-    *err = cudaGetLastError();
+    *err = launch_pdl(fn, dim3(nblocks), dim3(variant_threads(v)), smem, stream, p);
     if (*err != cudaSuccess) return CYTOF_ECUDA;
   }
   const int nout = bl.total + 2;
@@ -882,8 +883,8 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     pa.nout = nout;
     for (int q = 0; q < peer->world; ++q) pa.mailbox[q] = static_cast<unsigned char*>(peer->mailbox[q]);
   }
-  elbo_finalize_kernel<<<(nout * kFinLanes + 255) / 256, 256, 0, stream>>>(p, grad_block, ll_lqy, packed, pa);
-  *err = cudaGetLastError();
+  *err = launch_pdl(elbo_finalize_kernel, dim3((nout * kFinLanes + 255) / 256), dim3(256), 0, stream, p, grad_block, ll_lqy,
+                    packed, pa);
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
 

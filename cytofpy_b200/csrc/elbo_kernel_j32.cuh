@@ -61,6 +61,7 @@ constexpr int kJ32ConstFloats = 2 * (2 * 4) + 64 * (2 * 4);   // smem for mu pai
 template <int LM0, int LM1, bool NOISY, bool HAS_IDX>
 __global__ void __launch_bounds__(kThreads, CYTOF_J32_MINBLOCKS)
 elbo_fwdbwd_j32_kernel(const ElboParams p) {
+  pdl_enter();
   constexpr int NP0 = (LM0 + 1) / 2, NP1 = (LM1 + 1) / 2;   // component pairs per mixture
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];

@@ -154,6 +154,7 @@ __device__ __forceinline__ void constexpr_pair_max(const int q, const float2 v, 
 template <int LM0, int LM1, bool NOISY, bool HAS_IDX, bool MISSING>
 __global__ void __launch_bounds__(kThreads, 1)
 elbo_fwdbwd_mma_kernel(const ElboParams p) {
+  pdl_enter();
   constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;          // components, packed pairs
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];

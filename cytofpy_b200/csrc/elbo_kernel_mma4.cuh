@@ -35,6 +35,7 @@ constexpr int kQWarpFloats = 2 * 8 * kQTS + 2 * kQT * kQTS + 2 * kQT * 32 + 16 +
 template <int LM0, int LM1, bool NOISY, bool HAS_IDX, bool MISSING>
 __global__ void __launch_bounds__(kQThreads, 1)
 elbo_fwdbwd_mma4_kernel(const ElboParams p) {
+  pdl_enter();
   constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;          // components, packed pairs
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];

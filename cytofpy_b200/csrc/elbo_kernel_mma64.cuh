@@ -108,6 +108,7 @@ __device__ __forceinline__ float mix_backward(const float yv, const float mc0, c
 template <int LM0, int LM1, bool NOISY, bool HAS_IDX, int NTP, bool MISSING>
 __global__ void __launch_bounds__(kXThreads, 1)
 elbo_fwdbwd_mma64_kernel(const ElboParams p) {
+  pdl_enter();
   constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;
   constexpr int CPT = kXT / NTP, TP = 32 / CPT;            // cells and (padded) tail markers per tail pass
   constexpr int NU = kXT + NTP;                             // mixture units (warp passes) per tile

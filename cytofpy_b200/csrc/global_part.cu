@@ -123,6 +123,7 @@ global_fwd_elem_kernel(const GlobalParams p, const double* __restrict__ theta, c
                        double* __restrict__ real, double* __restrict__ eps_out, double* __restrict__ aux1,
                        double* __restrict__ aux2, float* __restrict__ globals, double* __restrict__ cta_part,
                        unsigned* ticket, unsigned long long* zmask, double* scalars, double* extra) {
+  pdl_enter();
   extern __shared__ double dyn[];
   __shared__ double sh[32];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(1024, 1)
 global_fwd_scan_kernel(const GlobalParams p, const double* aux1, const double* aux2, float* __restrict__ globals,
                        unsigned long long* __restrict__ zmask, const double* cta_part, double* __restrict__ scalars,
                        double* extra, const int staged) {
+  pdl_enter();
   extern __shared__ double dyn[];
   global_fwd_scan_body(p, aux1, aux2, globals, zmask, cta_part, scalars, extra, staged, dyn);
 }
@@ -304,6 +306,7 @@ __global__ void __launch_bounds__(kElemThreads)
 global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
                        double* __restrict__ aux2, const double* __restrict__ packed, double* __restrict__ greal,
                        int* __restrict__ flag, unsigned* ticket, double* extra, const long long* adam_step_dev) {
+  pdl_enter();
   extern __shared__ double dyn[];
   __shared__ double s_lvc[CYTOF_MAX_K];
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(1024, 1)
 global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, const double* aux1, const double* aux2,
                        const double* packed, double* __restrict__ greal, double* extra, const long long* adam_step_dev,
                        const int staged) {
+  pdl_enter();
   extern __shared__ double dyn[];
   global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, staged, dyn);
 }
@@ -460,6 +464,7 @@ global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const doubl
                    const double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
                    double* __restrict__ grad_out, double* __restrict__ out_scalars,
                    long long* step_dev, int* flag, int do_update, unsigned* ticket, const double* extra) {
+  pdl_enter();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const int R = p.roff[B_COUNT];
@@ -604,15 +609,17 @@ int launch_global_fwd(const cytof_global_desc* g, const double* theta, const dou
   double* extra = stash + 5 * (size_t)R + 2 * kElemCtas + 2;
   const size_t want = sizeof(double) * 2 * (size_t)R;
   const size_t fused = scan_smem_bytes((const void*)global_fwd_elem_kernel, 0, want);
+  const dim3 eg(kElemCtas), eb(kElemThreads);
   if (fused) {      // one launch: the last CTA of the element kernel runs the scans out of shared memory
-    global_fwd_elem_kernel<<<kElemCtas, kElemThreads, fused, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
-                                                                  stash + 4 * R, globals, stash + 5 * R, tickets, zm, scalars, extra);
+    *err = launch_pdl(global_fwd_elem_kernel, eg, eb, fused, s, p, theta, eps_in, stash, stash + R, stash + 3 * R,
+                      stash + 4 * R, globals, stash + 5 * R, tickets, zm, scalars, extra);
   } else {
-    global_fwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, eps_in, stash, stash + R, stash + 3 * R,
-                                                              stash + 4 * R, globals, stash + 5 * R, nullptr, zm, scalars, extra);
-    global_fwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash + 3 * R, stash + 4 * R, globals, zm, stash + 5 * R, scalars, extra, 0);
+    *err = launch_pdl(global_fwd_elem_kernel, eg, eb, 0, s, p, theta, eps_in, stash, stash + R, stash + 3 * R,
+                      stash + 4 * R, globals, stash + 5 * R, nullptr, zm, scalars, extra);
+    if (*err == cudaSuccess)
+      *err = launch_pdl(global_fwd_scan_kernel, dim3(1), dim3(1024), 0, s, p, stash + 3 * R, stash + 4 * R, globals, zm,
+                        stash + 5 * R, scalars, extra, 0);
   }
-  *err = cudaGetLastError();
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
 int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, const double* packed,
@@ -629,18 +636,21 @@ int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, 
   const long long* sd = reinterpret_cast<const long long*>(step_dev);
   const size_t want = sizeof(double) * (2 * (size_t)R + (size_t)blh.total + 2);
   const size_t fused = scan_smem_bytes((const void*)global_bwd_elem_kernel, 1, want);
+  const dim3 eg(kElemCtas), eb(kElemThreads);
   if (fused) {
-    global_bwd_elem_kernel<<<kElemCtas, kElemThreads, fused, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
-                                                                  stash + 2 * R, flag, tickets + 1, extra, sd);
+    *err = launch_pdl(global_bwd_elem_kernel, eg, eb, fused, s, p, stash, stash + 3 * R, stash + 4 * R, packed,
+                      stash + 2 * R, flag, tickets + 1, extra, sd);
   } else {
-    global_bwd_elem_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed,
-                                                              stash + 2 * R, flag, nullptr, extra, sd);
-    global_bwd_scan_kernel<<<1, 1024, 0, s>>>(p, stash, stash + 3 * R, stash + 4 * R, packed, stash + 2 * R, extra, sd, 0);
+    *err = launch_pdl(global_bwd_elem_kernel, eg, eb, 0, s, p, stash, stash + 3 * R, stash + 4 * R, packed,
+                      stash + 2 * R, flag, nullptr, extra, sd);
+    if (*err == cudaSuccess)
+      *err = launch_pdl(global_bwd_scan_kernel, dim3(1), dim3(1024), 0, s, p, stash, stash + 3 * R, stash + 4 * R, packed,
+                        stash + 2 * R, extra, sd, 0);
   }
-  global_adam_kernel<<<kElemCtas, kElemThreads, 0, s>>>(p, theta, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
-                                                        adam_v, grad_out, out_scalars,
-                                                        reinterpret_cast<long long*>(step_dev), flag, do_update, tickets + 2, extra);
-  *err = cudaGetLastError();
+  if (*err == cudaSuccess)
+    *err = launch_pdl(global_adam_kernel, eg, eb, 0, s, p, theta, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
+                      adam_v, grad_out, out_scalars, reinterpret_cast<long long*>(step_dev), flag, do_update, tickets + 2,
+                      extra);
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
 
