@@ -585,7 +585,8 @@ int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
 // device and kernel), else 0 = separate scan kernels reading global memory
 static size_t scan_smem_bytes(const void* fn, int which, size_t want) {
   static size_t granted[64][4] = {};
-  if (want > 200 * 1024) return 0;
+  static const bool unfused = [] { const char* e = getenv("CYTOF_GLOBAL_UNFUSED"); return e && e[0] == '1'; }();
+  if (unfused || want > 200 * 1024) return 0;      // the environment switch lets the tests drive the fallback path
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return want <= 48 * 1024 ? want : 0;
   if (want > 48 * 1024 && want > granted[dev][which]) {

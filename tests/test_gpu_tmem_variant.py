@@ -24,3 +24,16 @@ def test_parity_suite_with_tmem_dz_variant():
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert ' passed' in r.stdout
+
+
+def test_global_part_fallback_path_and_dependent_launch_option():
+    """csrc/global_part.cu runs the scans in the last CTA of the element kernels when their operands fit
+    in shared memory and as separate single-CTA kernels otherwise; CYTOF_GLOBAL_UNFUSED=1 forces the
+    second path.  CYTOF_PDL=1 launches every kernel of the step with programmatic stream serialisation
+    (csrc/common.cuh).  Both must pass the fused-step and step-loop suites."""
+    for extra in ({'CYTOF_GLOBAL_UNFUSED': '1'}, {'CYTOF_PDL': '1'}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_fused_step.py', 'tests/test_gpu_steploop.py',
+                            '-q', '-x'], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
+        assert ' passed' in r.stdout
