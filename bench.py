@@ -256,25 +256,46 @@ def run_ours(args, w, rank, world, local_rank):
         host_rng = np.random.default_rng(0)
         # the staged rows are sample-major and contiguous: sample i's rows are i*mb .. (i+1)*mb of y_dev
         idx_stage = [(torch.arange(i * mb, (i + 1) * mb, dtype=torch.int32) - i * n).to(dev) for i in range(I)]
-    for t in range(2 + max(3, args.steps // 2)):
+    n_e2e = 2 + max(3, args.steps // 2)
+    if mb is None:
+        # full batch: sample-by-sample upload overlapped with the per-cell kernels; the 40-byte result of
+        # every step is copied to pinned host memory and READ ON THE HOST ONE STEP LATE (what a training
+        # loop that logs the ELBO does), so the upload of step t+1 is already queued while step t computes
+        res_pin = torch.empty((2, 5), dtype=torch.float64).pin_memory()
+        res_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        seen = []
+        for t in range(n_e2e):
+            if t == 2:      # timed region starts with an empty pipeline
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            sc = fs.step_from_host(y_pin, no_missing=pin_clean)
+            res_pin[t & 1].copy_(sc, non_blocking=True)
+            res_ev[t & 1].record()
+            if t >= 1:
+                res_ev[(t - 1) & 1].synchronize()
+                seen.append(res_pin[(t - 1) & 1].tolist())
+        res_ev[(n_e2e - 1) & 1].synchronize()
+        seen.append(res_pin[(n_e2e - 1) & 1].tolist())
+        e1.record()
+        e1.synchronize()
+        assert len(seen) == n_e2e and all(v[0] == v[0] for v in seen), 'e2e: a step returned NaN'
+        e_ev.append((e0, e1))
+        e2e_div = n_e2e - 2
+    for t in range(0 if mb is None else n_e2e):
+        # minibatch: gather the step's rows on the host into a pinned staging buffer, ship them, step, read back
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        if mb is None:      # full batch: sample-by-sample upload overlapped with the per-cell kernel
-            _ = fs.step_from_host(y_pin, no_missing=pin_clean).tolist()
-            b.record()
-            e_ev.append((a, b))
-            continue
-        else:   # minibatch: gather the step's rows on the host into a pinned staging buffer, ship them
-            sel = torch.from_numpy(np.concatenate(
-                [host_rng.choice(n, mb, replace=False, shuffle=False) + i * n for i in range(I)]))
-            torch.index_select(y_host, 0, sel, out=stage)
-            eng.y_dev[:cells_step].copy_(stage, non_blocking=True)
-            idx = idx_stage
-        _ = fs.step(idx).tolist()                                # 40-byte read-back of elbo/ll/lp/lq
+        sel = torch.from_numpy(np.concatenate(
+            [host_rng.choice(n, mb, replace=False, shuffle=False) + i * n for i in range(I)]))
+        torch.index_select(y_host, 0, sel, out=stage)
+        eng.y_dev[:cells_step].copy_(stage, non_blocking=True)
+        _ = fs.step(idx_stage).tolist()                          # 40-byte read-back of elbo/ll/lp/lq
         b.record()
         e_ev.append((a, b))
     barrier()
-    e2e_ms = statistics.mean(a.elapsed_time(b) for a, b in e_ev[2:])
+    e2e_ms = (e_ev[0][0].elapsed_time(e_ev[0][1]) / e2e_div if mb is None
+              else statistics.mean(a.elapsed_time(b) for a, b in e_ev[2:]))
     if mb is not None:   # restore the resident matrix
         eng.y_dev.copy_(y_pin)
 

@@ -257,8 +257,11 @@ class FusedStep:
     def step_from_host(self, y_pinned, update=True, no_missing=False):
         """The same full-batch step with the data matrix in PINNED HOST memory (`y_pinned`:
         [sum N_i, J] fp32, NaN = missing): sample i is uploaded on a side stream while the per-cell
-        kernel of sample i-1 runs, so the PCIe copy and the compute overlap.  The per-sample packed
-        results are added (one tiny torch op) before the backward of the global part.
+        kernel of sample i-1 runs, so the PCIe copy and the compute overlap; the device holds two copies
+        of the matrix and alternates between them, so the upload of the NEXT call overlaps the tail of
+        this one (callers that read the returned scalars one step late keep the link saturated).  The
+        per-sample packed results are added (one tiny torch op) before the backward of the global part.
+        After the call `engine.y_dev` is the buffer just uploaded; a captured graph is released.
         `no_missing=True` is the caller's statement that `y_pinned` holds no NaN (checked once on
         the host by whoever owns the matrix); otherwise the imputation path stays compiled in."""
         m, eng, g = self.model, self.eng, self.g
@@ -273,13 +276,30 @@ class FusedStep:
             self._copy_stream = torch.cuda.Stream(self.dev)
             self._parts = torch.zeros((I, self.packed.numel()), dtype=F64, device=self.dev)
             self._ev = [torch.cuda.Event() for _ in range(I)]
+            # two device copies of the matrix: the upload of step t+1 starts while the kernels of step t
+            # still read the other one, so the PCIe link never waits for the tail of a step
+            self._ybuf = [eng.y_dev, torch.empty_like(eng.y_dev)]
+            self._yfree = [None, None]            # event: the last kernel that read the buffer has finished
+            self._ynext = 1 if eng.y_dev.data_ptr() == self._ybuf[0].data_ptr() else 0
         cs = self._copy_stream
-        cs.wait_stream(main)                      # the previous step no longer reads y_dev
+        bsel = self._ynext
+        self._ynext ^= 1
+        ybuf = self._ybuf[bsel]
+        if self._yfree[bsel] is not None:
+            cs.wait_event(self._yfree[bsel])
+        else:
+            cs.wait_stream(main)                  # first use: whatever was queued before may still read it
         rb = eng.row_base
         with torch.cuda.stream(cs):
             for i in range(I):
-                eng.y_dev[rb[i]:rb[i + 1]].copy_(y_pinned[rb[i]:rb[i + 1]], non_blocking=True)
+                ybuf[rb[i]:rb[i + 1]].copy_(y_pinned[rb[i]:rb[i + 1]], non_blocking=True)
                 self._ev[i].record(cs)
+        if eng.y_dev.data_ptr() != ybuf.data_ptr():
+            if getattr(self, 'graph', None) is not None:
+                self.release_graph()              # the captured step holds the other buffer's address
+            self._yfree[bsel ^ 1] = torch.cuda.Event()
+            self._yfree[bsel ^ 1].record(main)    # everything queued so far may read the buffer being left
+            eng.y_dev = ybuf                      # the resident matrix is now the one just uploaded
         stream = C.c_void_p(main.cuda_stream)
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.cytof_global_fwd_f64(
@@ -293,6 +313,8 @@ class FusedStep:
             counts[i] = eng.N_local[i]
             eng.fwdbwd_packed(Batch(counts, None, None, step=self.t), self.globals, self.zmask,
                               self._parts[i], [cg[j] if j == i else 0 for j in range(I)])
+        self._yfree[bsel] = torch.cuda.Event()
+        self._yfree[bsel].record(main)            # the per-cell kernels of this step are the last readers
         torch.sum(self._parts, 0, out=self.packed)
         if m.dist_group is not None:
             torch.distributed.all_reduce(self.packed, group=m.dist_group)

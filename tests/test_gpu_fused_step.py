@@ -118,3 +118,34 @@ def test_step_from_host_matches_resident_step():
         outs.append((sc.clone().cpu().numpy(), fs.grad.clone().cpu().numpy()))
     assert rel(outs[1][0][:4], outs[0][0][:4]) < 1e-9
     assert rel(outs[1][1], outs[0][1]) < 1e-6
+
+
+def test_step_from_host_alternates_device_buffers():
+    """consecutive host-fed steps upload into alternating device copies of the matrix (so the next upload
+    overlaps the tail of the previous step): every call must see exactly the matrix it was given, and the
+    resident matrix afterwards is the last one uploaded (a captured graph of the old address is dropped)."""
+    c = Case('i_cfg4like_trained')
+    dev = torch.device('cuda', 0)
+    y0 = torch.cat([t.float() for t in c.y], 0)
+    mats = [y0, y0 * 0.5, y0 + 0.25, y0 * 0.5]
+    idx = [range(n) for n in c.N]
+    ref = []
+    for ymat in mats:                      # resident reference: a fresh model per matrix, same step counter
+        mod = build_model(c, dev, noise='philox')
+        fs = FusedStep(mod, lr=0.05, seed=11)
+        mod.engine.y_dev.copy_(ymat.to(dev))
+        for _ in range(len(ref) + 1):      # advance the step counter without touching the parameters
+            fs.step(idx, update=False)
+        ref.append(fs.step(idx, update=False).clone().cpu().numpy())
+    mod = build_model(c, dev, noise='philox')
+    fs = FusedStep(mod, lr=0.05, seed=11)
+    fs.step(idx, update=False)             # step 1 (capture() would otherwise take a training step first)
+    fs.capture(None)
+    assert fs.graph is not None
+    got = []
+    for ymat in mats:
+        got.append(fs.step_from_host(ymat.pin_memory(), update=False).clone().cpu().numpy())
+    assert fs.graph is None
+    for a, b in zip(got, ref):
+        assert rel(a[:4], b[:4]) < 1e-9
+    assert torch.equal(mod.engine.y_dev.cpu().nan_to_num(), mats[-1].nan_to_num())
