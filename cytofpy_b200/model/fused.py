@@ -254,6 +254,33 @@ class FusedStep:
         if self.peers is not None:
             self.peers.desc.seq_dev = None
 
+    def use_host_matrix(self, y_pinned):
+        """Leave the data matrix with the caller: `y_pinned` ([sum N_i, J] fp32, PINNED host memory, NaN =
+        missing, same row layout as the resident copy) becomes the matrix the per-cell kernel reads.  A
+        pinned allocation is addressable from the device (unified addressing), so the kernel's row gather
+        (cp.async, 128-byte rows) pulls exactly the minibatch's rows over PCIe -- no host-side gather, no
+        staging copy, and `capture()` / `graph_step()` work unchanged (device sampler included).  Meant
+        for minibatch steps; a full-batch step would stream the whole matrix through the kernel at PCIe
+        speed (`step_from_host` overlaps that with compute instead).  `use_device_matrix()` undoes it."""
+        eng = self.eng
+        if not (y_pinned.is_pinned() and y_pinned.dtype == torch.float32 and y_pinned.is_contiguous()
+                and tuple(y_pinned.shape) == tuple(eng.y_dev.shape)):
+            raise ValueError('use_host_matrix: need a pinned, contiguous fp32 [sum N_i, J] matrix')
+        if getattr(self, 'graph', None) is not None:
+            self.release_graph()
+        if not hasattr(self, '_y_resident'):
+            self._y_resident = eng.y_dev
+        self._y_host = y_pinned                   # keep the allocation alive
+        eng.y_dev = y_pinned
+
+    def use_device_matrix(self):
+        """back to the device-resident copy of the matrix"""
+        if hasattr(self, '_y_resident'):
+            if getattr(self, 'graph', None) is not None:
+                self.release_graph()
+            self.eng.y_dev = self._y_resident
+            del self._y_resident, self._y_host
+
     def step_from_host(self, y_pinned, update=True, no_missing=False):
         """The same full-batch step with the data matrix in PINNED HOST memory (`y_pinned`:
         [sum N_i, J] fp32, NaN = missing): sample i is uploaded on a side stream while the per-cell

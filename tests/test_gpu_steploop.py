@@ -193,6 +193,35 @@ def test_cuda_graph_step_equals_host_driven_steps(mb, nan_rate):
     assert a == ref.step(idx).tolist()
 
 
+@pytest.mark.parametrize('nan_rate', [0.2, 0.0])
+def test_graph_steps_reading_the_matrix_from_pinned_host_memory(nan_rate):
+    """FusedStep.use_host_matrix: the per-cell kernel gathers the minibatch rows straight from a pinned host
+    matrix (no staging copy); the captured step must reproduce the device-resident one bit for bit."""
+    from cytofpy_b200.model.fused import FusedStep
+    dev = torch.device('cuda', 0)
+    mb, steps = 200, 5
+    ref_mod = _small_model(dev, nan_rate)
+    ref = FusedStep(ref_mod, lr=0.05, seed=3)
+    ref.capture(mb)
+    hist_ref = [ref.graph_step().tolist() for _ in range(steps)]
+    mod = _small_model(dev, nan_rate)
+    fs = FusedStep(mod, lr=0.05, seed=3)
+    y_pin = mod.engine.y_dev.cpu().pin_memory()
+    fs.capture(mb)                       # takes its first (host-driven) step from the resident copy, like `ref`
+    fs.use_host_matrix(y_pin)
+    assert fs.graph is None
+    mod.engine_resident = fs._y_resident
+    fs._y_resident.zero_()               # the resident copy must not be read from here on
+    fs.capture(mb)
+    hist = [fs.graph_step().tolist() for _ in range(steps)]
+    assert hist == hist_ref
+    assert torch.equal(fs.theta, ref.theta)
+    fs.use_device_matrix()
+    assert mod.engine.y_dev.is_cuda
+    with pytest.raises(ValueError):
+        fs.use_host_matrix(y_pin[:-1])
+
+
 def test_multi_sample_sampler_equals_per_sample_calls():
     """cytof_sample_minibatch_multi (one launch for all samples, host step or device step counter)
     draws exactly the indices of the per-sample cytof_sample_minibatch calls."""
