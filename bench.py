@@ -139,7 +139,9 @@ def run_reference(args, w, rank, world):
     if rank != 0:
         return
     per = min(w['n'], 4000 if w['mb'] is None else w['n'])
-    v, cores, cells, med = time_cpu_port(w, args.steps, args.warmup, per)
+    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    v, cores, cells, med = time_cpu_port(w, args.steps, args.warmup, per, threads=threads)
     sample = 'oracle port of reference update (fp64 torch CPU, autograd, Adam) on %d cells/step ' \
              '(%d samples x %d%s) at the workload J/K/L' % (cells, w['I'], per,
                                                            '' if w['mb'] is None else ', minibatch %d' % w['mb'])
