@@ -40,9 +40,10 @@ def test_adam_kernel_matches_torch_adam_and_scrubs_nan():
         use_dev_counter = t >= 4
         if t == 4:
             step_dev.fill_(3)
-        _lib.check(lib.cytof_adam_step_f64(_p(p), _p(grad.to(dev)), _p(m), _p(v), n, n_scrub, -0.001, 0.1,
+        grad_dev = grad.to(dev)            # held until the synchronize below (the call is asynchronous)
+        _lib.check(lib.cytof_adam_step_f64(_p(p), _p(grad_dev), _p(m), _p(v), n, n_scrub, -0.001, 0.1,
                                            0.9, 0.999, 1e-8, t, _p(step_dev) if use_dev_counter else _p(None),
-                                           _p(flag), C.c_void_p(0)))
+                                           _p(flag), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         torch.cuda.synchronize()
         assert flag.item() == (1 if t >= 3 else 0)
         assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-12, atol=1e-14), t
