@@ -179,12 +179,15 @@ class FusedStep:
         return self.scalars
 
     # ------------------------------------------------------------------ CUDA graph
-    def capture(self, minibatch_size=None):
+    def capture(self, minibatch_size=None, repeat=1):
         """Capture one whole training step -- device minibatch sampler, global forward, fused
         per-cell kernel + finalise (+ all-reduce), global backward + Adam -- in ONE CUDA graph.
         All step-dependent inputs (Philox counters of the global and per-cell noise, sampler key,
         Adam step, peer sequence number) are read on the device from `step_dev`, which the last
-        kernel of the step bumps, so `graph_step()` is a bare replay (reference fit.py:91-106)."""
+        kernel of the step bumps, so `graph_step()` is a bare replay (reference fit.py:91-106).
+        `repeat` > 1 additionally captures `repeat` consecutive steps as one graph, each followed by a
+        copy of its [elbo, ll, lp, lq, scrubbed] into row j of `self.hist`: `graph_steps()` then costs the
+        host one launch and one read-back per `repeat` steps."""
         m, eng, g = self.model, self.eng, self.g
         I = eng.I
         counts = [n if (minibatch_size is None or minibatch_size >= n) else int(minibatch_size)
@@ -235,7 +238,25 @@ class FusedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
+        self.graph_multi, self._repeat = None, int(repeat)
+        if self._repeat > 1:
+            self.hist = torch.zeros((self._repeat, 5), dtype=F64, device=self.dev)
+            self.graph_multi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_multi):
+                for j in range(self._repeat):
+                    body()
+                    self.hist[j].copy_(self.scalars)
         return self
+
+    def graph_steps(self):
+        """Replay the `repeat` captured consecutive steps; returns the device tensor [repeat, 5] of their
+        [elbo, ll, lp, lq, scrubbed] rows."""
+        self.graph_multi.replay()
+        self.t += self._repeat
+        if self.peers is not None:
+            self.peers.seq += self._repeat
+        self.launches += self._repeat * (self._graph_launches + 1)
+        return self.hist
 
     def graph_step(self):
         """Replay the captured step; returns the device tensor [elbo, ll, lp, lq, scrubbed]."""
@@ -249,6 +270,7 @@ class FusedStep:
     def release_graph(self):
         """back to host-driven steps (`step`)"""
         self.graph = None
+        self.graph_multi = None
         self.g.step_dev = None
         self.eng.step_dev = None
         if self.peers is not None:

@@ -68,7 +68,8 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         y_mean_init=-3.0, y_sd_init=0.1, trace_every=None, eps_conv=1e-6, tau=0.1,
         backup_every=10, y_quantiles=[0, 35, 70], p_bounds=[.05, .8, .05], scale=1,
         use_stick_break=True, model_noisy=True, init_mp=None, verbose=1, flush=True,
-        K=30, L=None, device=None, sampler='device', noise='philox', fused=True, graph=True):
+        K=30, L=None, device=None, sampler='device', noise='philox', fused=True, graph=True,
+        pipeline=True):
     """reference fit.py:50-147, same arguments and the same returned dict keys
     ('elbo', 'trace', 'mp', 'tau', 'vae', 'use_stick_break', 'y', 'priors', 'model_noisy').
 
@@ -78,7 +79,12 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
     (True: the whole step runs as 4-5 kernel launches, cytofpy_b200/model/fused.py, when the
     priors are of the default families; False / other priors: torch autograd + torch Adam
     around the fused per-cell kernel), graph (True: with the fused path and the device sampler,
-    every step after the first is ONE CUDA-graph replay, FusedStep.capture)."""
+    every step after the first is ONE CUDA-graph replay, FusedStep.capture), pipeline (True: on the
+    graph path the steps between two backup / trace snapshots run as ONE graph of min(backup_every,
+    trace_every) consecutive steps with one read-back for all of them, so the GPU never idles on the
+    host round trip; histories and snapshots are identical to pipeline=False -- only when the
+    convergence rule fires inside such a chunk have its remaining steps already been applied to the
+    live imputation parameters returned in 'vae')."""
     print('scale: {}'.format(scale))
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -107,8 +113,64 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
     best_mp = copy.deepcopy(model.mp)
     best_vae = copy.deepcopy(model.y_vae)
     elbo_hist, trace = [], []
-    for t in range(max_iter + 1):
-        replay = stepper is not None and graph and sampler == 'device' and t >= 1
+    state = {'best_mp': best_mp, 'best_vae': best_vae}
+
+    def finish(t, elbo_t, ll, lp, lq, fixed_grad):
+        """bookkeeping of step t (reference fit.py:109-141); True = stop"""
+        elbo_hist.append(elbo_t)
+        elbo_good = not fixed_grad
+        if t % print_freq == 0:
+            print('{} | {}/{} | elbo: {:.3f} | ll: {:.3f} | lp: {:.3f} | lq: {:.3f}'.format(
+                datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"), t, max_iter,
+                elbo_hist[-1] / model.Nsum, ll / model.Nsum, lp / model.Nsum, lq / model.Nsum))
+        if backup_every > 0 and t % backup_every == 0 and elbo_good:
+            state['best_mp'] = copy.deepcopy(model.mp)
+            state['best_vae'] = model.y_vae
+        if trace_every > 0 and t % trace_every == 0 and elbo_good:
+            trace.append({key: copy.deepcopy(model.mp[key]) for key in model.mp})
+        if t > 10 and abs(elbo_hist[-1] / elbo_hist[-2] - 1) < eps_conv:
+            print('Convergence suspected! Ending optimizer early.')
+            return True
+        if flush:
+            sys.stdout.flush()
+        return False
+
+    def snapshots(t):
+        return (backup_every > 0 and t % backup_every == 0) or (trace_every > 0 and t % trace_every == 0)
+
+    # `pipeline`: between two snapshot steps nothing on the host depends on the parameters, so those steps
+    # run as ONE graph of `chunk` consecutive steps (FusedStep.graph_steps) and their results are read back
+    # together; a chunk always ENDS on the snapshot step, so every backup / trace copy holds exactly the
+    # parameters the reference's loop would have copied
+    replayable = stepper is not None and graph and sampler == 'device'
+    chunk = 1
+    if pipeline and replayable:
+        every = [v for v in (backup_every, trace_every) if v > 0]
+        chunk = min(min(every) if every else 16, 32)
+    t = 0
+    while t <= max_iter:
+        replay = replayable and t >= 1
+        if replay and stepper.graph is None:
+            stepper.capture(minibatch_size, repeat=chunk)
+        run = 1
+        if replay and chunk > 1:        # steps up to and including the next snapshot step (or the last one)
+            s_next = t
+            while s_next < max_iter and not snapshots(s_next):
+                s_next += 1
+            run = s_next - t + 1
+        if replay and chunk > 1 and run >= chunk:
+            rows = stepper.graph_steps().tolist()                 # one launch, one read-back per chunk
+            stop = False
+            for j, (elbo_t, ll, lp, lq, scrubbed) in enumerate(rows):
+                if scrubbed != 0.0:
+                    print("WARNING: Setting a nan gradient to zero!")
+                if finish(t + j, elbo_t, ll, lp, lq, scrubbed != 0.0):
+                    stop = True         # the remaining steps of the chunk have run; their results are dropped
+                    break
+            t += chunk
+            if stop:
+                break
+            continue
         if replay:
             idx = None      # the captured graph draws its own minibatch on the device
         elif sampler == 'numpy':
@@ -117,35 +179,18 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         else:
             idx = device_minibatch(model, minibatch_size, t, seed)
         if stepper is not None:
-            if replay:
-                if stepper.graph is None:
-                    stepper.capture(minibatch_size)
-                out_t = stepper.graph_step()
-            else:
-                out_t = stepper.step(idx)
+            out_t = stepper.graph_step() if replay else stepper.step(idx)
             elbo_t, ll, lp, lq, scrubbed = out_t.tolist()     # one 40-byte read-back
             fixed_grad = scrubbed != 0.0
             if fixed_grad:
                 print("WARNING: Setting a nan gradient to zero!")
-            elbo_hist.append(elbo_t)
         else:
             elbo, fixed_grad, ll, lp, lq = update(optimizer, model, idx)
-            elbo_hist.append(elbo.item())
-        elbo_good = not fixed_grad
-        if t % print_freq == 0:
-            print('{} | {}/{} | elbo: {:.3f} | ll: {:.3f} | lp: {:.3f} | lq: {:.3f}'.format(
-                datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"), t, max_iter,
-                elbo_hist[-1] / model.Nsum, ll / model.Nsum, lp / model.Nsum, lq / model.Nsum))
-        if backup_every > 0 and t % backup_every == 0 and elbo_good:
-            best_mp = copy.deepcopy(model.mp)
-            best_vae = model.y_vae
-        if trace_every > 0 and t % trace_every == 0 and elbo_good:
-            trace.append({key: copy.deepcopy(model.mp[key]) for key in model.mp})
-        if t > 10 and abs(elbo_hist[-1] / elbo_hist[-2] - 1) < eps_conv:
-            print('Convergence suspected! Ending optimizer early.')
+            elbo_t = elbo.item()
+        if finish(t, elbo_t, ll, lp, lq, fixed_grad):
             break
-        if flush:
-            sys.stdout.flush()
+        t += 1
+    best_mp, best_vae = state['best_mp'], state['best_vae']
     return {'elbo': elbo_hist, 'trace': trace, 'mp': best_mp, 'tau': tau, 'vae': best_vae,
             'use_stick_break': use_stick_break, 'y': y, 'priors': str(model.priors),
             'model_noisy': model_noisy}

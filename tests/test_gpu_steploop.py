@@ -109,6 +109,32 @@ def test_fit_runs_and_improves_elbo(capsys):
     assert out['trace'][0]['W'].dist().mean.shape == (3, 9)
 
 
+def test_fit_with_run_ahead_equals_step_by_step_fit(capsys):
+    """fit(pipeline=True) queues step t+1 before it reads the result of step t (except around snapshots):
+    ELBO history, trace and backup must be exactly those of the step-by-step loop."""
+    outs = []
+    for pipeline in (True, False):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        data = cy.util.simdata_with_missing_values(N=[300, 100, 200], L0=3, L1=3, J=8, a_W=[100.] * 5, seed=0,
+                                                   rate=0.1)
+        y = [t.clone() for t in data['data']['y']]
+        pri = cy.model.default_priors(y, K=10, L=[3, 3], y_bounds=[-5., -3.5, -2.])
+        outs.append(cy.model.fit(y, max_iter=47, lr=1e-1, print_freq=40, eps_conv=1e-12, priors=pri,
+                                 minibatch_size=100, tau=0.1, verbose=0, seed=1, backup_every=7,
+                                 trace_every=5, pipeline=pipeline))
+    a, b = outs
+    assert a['elbo'] == b['elbo'] and len(a['elbo']) == 48
+    assert len(a['trace']) == len(b['trace']) == 10
+    for ta, tb in zip(a['trace'], b['trace']):
+        for key in ta:
+            assert torch.equal(ta[key].vp, tb[key].vp)
+    for key in a['mp']:
+        assert torch.equal(a['mp'][key].vp, b['mp'][key].vp)
+    for va, vb in zip(a['vae'], b['vae']):
+        assert torch.equal(va.mean, vb.mean) and torch.equal(va.log_sd, vb.log_sd)
+
+
 def test_posterior_label_sampler_matches_oracle():
     """post_proc.theta + post_proc.sample (reference post_proc/lam_post.py:6-55): class
     probabilities vs the fp64 oracle, and the categorical draws vs those probabilities."""
