@@ -35,7 +35,7 @@ constexpr int kTile = 8;                 // cells per warp iteration (= N of the
 constexpr int kTS = 36;                  // row stride of the per-warp tiles: conflict-free ldmatrix
 constexpr int kTileFloats = kTile * kTS;
 // per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
-constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 32 + 2 * kTile * 32 + kTile * 32 + kMmaUFloats;
+constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 32 + 2 * kTile * 32 + 12 * 32 + kMmaUFloats;   // sW: 12 rows (Philox staging)
 constexpr int kMmaZFloats = 2 * 8 * 32 * 4 + kMmaHdrFloats;     // A-fragment tables of Z^T and Z (+ header)
 
 
@@ -171,9 +171,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   float* sR1 = sR0 + kTile * 32;           // [8][32] 1/S1
   float* sS = sR1 + kTile * 32;            // [0..7] fac*rho, [8..15] fac*(1-rho), [16..23] fac*rho/sum_k e_k per cell
   float* sYb = sS + 32;                    // [2][8][32] y rows, double buffered
-  float* sW = sYb + 2 * kTile * 32;        // [8][32] sum_l w d (imputation gradient)
+  float* sW = sYb + 2 * kTile * 32;        // [8][32] sum_l w d (imputation gradient); [12][32] normals during the pre-pass
 #if CYTOF_TMEM_DZ
-  unsigned char* sUA = reinterpret_cast<unsigned char*>(sW + kTile * 32);   // [2][2 KB] A = [D_hi ; D_lo] (64 x 8), K-major
+  unsigned char* sUA = reinterpret_cast<unsigned char*>(sW + 12 * 32);   // [2][2 KB] A = [D_hi ; D_lo] (64 x 8), K-major
   unsigned char* sUB = sUA + 2 * 2048;                                      // [2][2 KB] B = [g_hi ; g_lo] (64 x 8)
   unsigned long long* mbars = reinterpret_cast<unsigned long long*>(smem + 2 * 8 * 32 * 4) + 2 * warp;   // [2] per warp
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + 2 * 8 * 32 * 4 + 32);
@@ -187,9 +187,16 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   const int lb = (int)blockIdx.x - p.blk_begin[i];
   const long long cb = p.cell_begin[i];
   const long long Bi = p.cell_begin[i + 1] - cb;
-  const long long c_lo = Bi * lb / nb, c_hi = Bi * (lb + 1) / nb;
   const long long row_base = p.row_base[i];
   const unsigned long long grow_base = (unsigned long long)p.row_global[i];
+  // this CTA's cells [c_lo, c_hi) of the sample.  Full batch: the cut points are moved down to a global row
+  // that is a multiple of 8, so that the 8-cell tiles coincide with two 4-row Philox blocks (pre-pass)
+  auto cut = [&](const long long q) -> long long {
+    long long x = Bi * q / nb;
+    if (!HAS_IDX && q > 0 && q < nb) x -= (long long)((grow_base + (unsigned long long)x) & 7ull);
+    return x < 0 ? 0 : x;
+  };
+  const long long c_lo = cut(lb), c_hi = cut(lb + 1);
 
   // ---------------- Z fragment tables (once per CTA) ----------------
   {
@@ -354,7 +361,28 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       mmask |= (yr != yr) ? (1u << u) : 0u;
     }
     amask = __reduce_or_sync(FULL, mmask);       // cells of the tile with at least one missing marker
-    if (amask) {
+    if (!HAS_IDX && amask && p.noise_mode != CYTOF_NOISE_EXTERNAL) {
+      // consecutive rows: the tile lies in 2 (aligned) or 3 Philox blocks of 4 global rows.  Their normals go
+      // to a [12][32] staging area (row = global row - 4 grp0) and the NaNs are replaced by plain copies.
+      const unsigned long long grow0 = grow_base + (unsigned long long)(first_row + tn);
+      const unsigned a = (unsigned)grow0 & 3u;
+      const unsigned long long grp0 = grow0 >> 2;
+      const int ng = (int)((a + kTile + 3u) >> 2);
+#pragma unroll 1      // a real loop: ONE copy of the Philox rounds in the instruction stream
+      for (int gi = 0; gi < ng; ++gi) {
+        const int u0 = 4 * gi - (int)a;          // first cell of the block (may be negative)
+        const unsigned gm = (u0 >= 0 ? (0xfu << u0) : (0xfu >> -u0)) & 0xffu;
+        if (!(amask & gm)) continue;             // warp-uniform: no cell of this block misses anything
+        float nz[4];
+        philox_normal4(p.seed, elbo_step(p), grp0 + (unsigned long long)gi, lane, nz);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sW[(4 * gi + w) * 32 + lane] = nz[w];
+      }
+      const float* nzr = sW + a * 32 + lane;     // every lane reads back its own column only
+#pragma unroll
+      for (int u = 0; u < kTile; ++u)
+        if ((mmask >> u) & 1u) src[u * 32 + lane] = nzr[u * 32];
+    } else if (amask) {
       unsigned long long grp_c = ~0ull;          // Philox block in the cache: 4 consecutive global rows
       float nz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1      // a real loop: ONE copy of the Philox rounds in the instruction stream
