@@ -78,6 +78,60 @@ def _worker(rank, world, port, out_dir, mode):
     dist.destroy_process_group()
 
 
+def _graph_worker(rank, world, port, out_dir):
+    """multi-step CUDA graph (FusedStep.capture(repeat=3) / graph_steps) with the fused peer all-reduce
+    against single-step replays: same rows, same parameters, on both ranks"""
+    import cytofpy_b200 as cy
+    from cytofpy_b200.model.fused import FusedStep
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    c = Case(CASE)
+    lo = [n * rank // world for n in c.N]
+    hi = [n * (rank + 1) // world for n in c.N]
+    pri = cy.model.default_priors(c.y, K=c.K, L=[c.L0, c.L1], y_bounds=[-5., -3.5, -2.])
+    out = {}
+    for tag, repeat in (('multi', 3), ('single', 1)):
+        torch.manual_seed(5)
+        y = [t[a:b].clone() for t, a, b in zip(c.y, lo, hi)]
+        mod = cy.model.Model(y=y, priors=pri, tau=c.tau, verbose=-1, use_stick_break=c.stick,
+                             model_noisy=c.noisy, scale=c.scale, device=dev, noise='philox', seed=9,
+                             N_global=c.N, row_global=lo, dist_group=dist.group.WORLD)
+        fs = FusedStep(mod, lr=0.05, seed=9, allreduce='peer')
+        assert fs.peers is not None
+        rows = [fs.step([np.arange(b - a) for a, b in zip(lo, hi)]).tolist()]
+        fs.capture(None, repeat=repeat)
+        if repeat > 1:
+            for _ in range(2):
+                rows += fs.graph_steps().tolist()
+        else:
+            for _ in range(6):
+                rows.append(fs.graph_step().tolist())
+        assert fs.t == 7 and fs.peers.seq == 7
+        out[tag + '_rows'] = np.array(rows)
+        out[tag + '_theta'] = fs.theta.cpu().numpy().copy()
+        torch.cuda.synchronize()
+        dist.barrier()
+        fs.peers.close()
+    np.savez(os.path.join(out_dir, 'graph_rank%d.npz' % rank), **out)
+    dist.destroy_process_group()
+
+
+def test_multi_step_graph_with_peer_allreduce_two_ranks(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    world = 2
+    mp.spawn(_graph_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), 'graph_rank%d.npz' % r)) for r in range(world)]
+    for o in outs:
+        assert np.isfinite(o['multi_rows']).all() and o['multi_rows'].shape == (7, 5)
+        assert np.array_equal(o['multi_rows'], o['single_rows'])
+        assert np.array_equal(o['multi_theta'], o['single_theta'])
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
 def _run(tmp_path, mode):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
