@@ -64,6 +64,36 @@ def device_minibatch(mod, minibatch_size, step, seed):
     return out
 
 
+def is_snapshot_step(t, backup_every, trace_every):
+    """steps at which fit copies the parameters (reference fit.py:117-127)"""
+    return (backup_every > 0 and t % backup_every == 0) or (trace_every > 0 and t % trace_every == 0)
+
+
+def chunk_length(backup_every, trace_every, cap=32):
+    """steps per multi-step graph: the smaller snapshot period (a chunk must END on a snapshot step)"""
+    every = [v for v in (backup_every, trace_every) if v > 0]
+    return max(1, min(min(every) if every else 16, cap))
+
+
+def run_length(t, max_iter, backup_every, trace_every):
+    """number of steps from t up to and including the next snapshot step (or the last step)"""
+    s = t
+    while s < max_iter and not is_snapshot_step(s, backup_every, trace_every):
+        s += 1
+    return s - t + 1
+
+
+def step_schedule(max_iter, backup_every, trace_every, chunk):
+    """[(first step, number of steps)] as the pipelined fit loop issues them: step 0 alone (host-driven),
+    then a chunk of `chunk` steps wherever no snapshot step lies strictly inside it, single steps elsewhere"""
+    out, t = [], 0
+    while t <= max_iter:
+        n = chunk if (t >= 1 and chunk > 1 and run_length(t, max_iter, backup_every, trace_every) >= chunk) else 1
+        out.append((t, n))
+        t += n
+    return out
+
+
 def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=10, seed=1,
         y_mean_init=-3.0, y_sd_init=0.1, trace_every=None, eps_conv=1e-6, tau=0.1,
         backup_every=10, y_quantiles=[0, 35, 70], p_bounds=[.05, .8, .05], scale=1,
@@ -135,30 +165,18 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
             sys.stdout.flush()
         return False
 
-    def snapshots(t):
-        return (backup_every > 0 and t % backup_every == 0) or (trace_every > 0 and t % trace_every == 0)
-
     # `pipeline`: between two snapshot steps nothing on the host depends on the parameters, so those steps
     # run as ONE graph of `chunk` consecutive steps (FusedStep.graph_steps) and their results are read back
     # together; a chunk always ENDS on the snapshot step, so every backup / trace copy holds exactly the
     # parameters the reference's loop would have copied
     replayable = stepper is not None and graph and sampler == 'device'
-    chunk = 1
-    if pipeline and replayable:
-        every = [v for v in (backup_every, trace_every) if v > 0]
-        chunk = min(min(every) if every else 16, 32)
+    chunk = chunk_length(backup_every, trace_every) if (pipeline and replayable) else 1
     t = 0
     while t <= max_iter:
         replay = replayable and t >= 1
         if replay and stepper.graph is None:
             stepper.capture(minibatch_size, repeat=chunk)
-        run = 1
-        if replay and chunk > 1:        # steps up to and including the next snapshot step (or the last one)
-            s_next = t
-            while s_next < max_iter and not snapshots(s_next):
-                s_next += 1
-            run = s_next - t + 1
-        if replay and chunk > 1 and run >= chunk:
+        if replay and chunk > 1 and run_length(t, max_iter, backup_every, trace_every) >= chunk:
             rows = stepper.graph_steps().tolist()                 # one launch, one read-back per chunk
             stop = False
             for j, (elbo_t, ll, lp, lq, scrubbed) in enumerate(rows):

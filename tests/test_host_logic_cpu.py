@@ -122,3 +122,26 @@ def test_readcb_roundtrip(tmp_path):
     assert torch.isnan(d['y'][0][0, 1]) and d['m'][0][0, 1]
     cy.util.preprocess(d, rm_cells_below=-6.0)
     assert d['N'] == [1, 1] and d['y'][0].shape == (1, 2)
+
+
+@pytest.mark.parametrize('max_iter,backup_every,trace_every', [
+    (1000, 10, 20), (47, 7, 5), (30, 10, 0), (25, 0, 0), (12, 1, 3), (100, 64, 50), (5, 10, 10), (0, 10, 10)])
+def test_pipelined_fit_schedule_never_runs_past_a_snapshot(max_iter, backup_every, trace_every):
+    """fit(pipeline=True) replays multi-step graphs between parameter snapshots (train.py): the schedule must
+    cover steps 0..max_iter exactly once, start host-driven, and a snapshot step may only be the LAST step of
+    a chunk -- otherwise the backup / trace copies would hold later parameters than the reference's."""
+    from cytofpy_b200.model import train
+    chunk = train.chunk_length(backup_every, trace_every)
+    assert 1 <= chunk <= 32
+    sched = train.step_schedule(max_iter, backup_every, trace_every, chunk)
+    assert sched[0] == (0, 1)
+    covered = [t + j for t, n in sched for j in range(n)]
+    assert covered == list(range(max_iter + 1))
+    for t, n in sched:
+        assert n in (1, chunk)
+        for j in range(n - 1):
+            assert not train.is_snapshot_step(t + j, backup_every, trace_every), (t, n, j)
+    periods = [v for v in (backup_every, trace_every) if v > 0]
+    if chunk > 1 and max_iter >= 4 * chunk and all(v % chunk == 0 for v in periods):
+        # aligned snapshot periods (the defaults: 10 and max_iter / 50): all but the edges run inside chunks
+        assert sum(n for _, n in sched if n > 1) >= max_iter + 1 - 2 * chunk
