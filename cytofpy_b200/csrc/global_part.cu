@@ -101,8 +101,8 @@ global_fwd_scan_body(const GlobalParams& p, const double* aux1, const double* au
                      double* extra, const int staged, double* dyn);
 __device__ __forceinline__ void
 global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, const double* aux1, const double* aux2,
-                     const double* packed, double* __restrict__ greal, double* extra, const long long* adam_step_dev,
-                     const int staged, double* dyn);
+                     const double* packed, double* __restrict__ greal, double* extra, long long* adam_step_dev,
+                     const int do_update, const int staged, double* dyn);
 
 // true in exactly one CTA of the grid: the one that finishes last (its threads then see everything the
 // other CTAs wrote before their ticket); the ticket is left at 0 for the next launch
@@ -305,7 +305,8 @@ global_fwd_scan_kernel(const GlobalParams p, const double* aux1, const double* a
 __global__ void __launch_bounds__(kElemThreads)
 global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, const double* __restrict__ aux1,
                        double* __restrict__ aux2, const double* __restrict__ packed, double* __restrict__ greal,
-                       int* __restrict__ flag, unsigned* ticket, double* extra, const long long* adam_step_dev) {
+                       int* __restrict__ flag, unsigned* ticket, double* extra, long long* adam_step_dev,
+                       double* out_scalars, const int do_update) {
   pdl_enter();
   extern __shared__ double dyn[];
   __shared__ double s_lvc[CYTOF_MAX_K];
@@ -313,7 +314,10 @@ global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, co
   const int R = p.roff[B_COUNT];
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const double* __restrict__ G = packed;
-  if (flag && blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {      // the Adam kernel (next launch) raises both when it scrubs a NaN
+    if (flag) *flag = 0;
+    out_scalars[4] = 0.0;
+  }
 
   // ---- (0) logit of cumprod(v): left in the stash by the forward scan
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_lvc[k] = extra[CYTOF_MAX_K + k];
@@ -352,15 +356,15 @@ global_bwd_elem_kernel(const GlobalParams p, const double* __restrict__ real, co
       default: break;                    // delta0 / delta1 / alpha / v: scan kernel
     }
   }
-  if (ticket && last_cta_done(ticket)) global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, 1, dyn);
+  if (ticket && last_cta_done(ticket)) global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, do_update, 1, dyn);
 }
 
 // (2) one CTA: suffix scans (cumsum / cumprod / stick-breaking backward), adds and multiplies only
 __device__ __forceinline__ void
 global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, const double* aux1,
                      const double* aux2, const double* packed,
-                     double* __restrict__ greal, double* extra, const long long* adam_step_dev, const int staged,
-                     double* dyn) {
+                     double* __restrict__ greal, double* extra, long long* adam_step_dev, const int do_update,
+                     const int staged, double* dyn) {
   __shared__ double s_vc[CYTOF_MAX_K], s_gvc[CYTOF_MAX_K], s_suf[CYTOF_MAX_K], s_red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -381,6 +385,9 @@ global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, con
     const long long step = adam_step_dev ? (*adam_step_dev + 1) : p.step_host;
     extra[2 * CYTOF_MAX_K] = 1.0 - pow(p.beta1, (double)step);
     extra[2 * CYTOF_MAX_K + 1] = sqrt(1.0 - pow(p.beta2, (double)step));
+    // every reader of the device step counter of this step has finished (the Adam kernel takes its bias
+    // corrections from `extra`): bump it here, so the Adam kernel needs no grid-wide rendezvous
+    if (adam_step_dev && do_update) *adam_step_dev += 1;
   }
 
   if (tid == 0) {
@@ -450,11 +457,11 @@ global_bwd_scan_body(const GlobalParams& p, const double* __restrict__ real, con
 
 __global__ void __launch_bounds__(1024, 1)
 global_bwd_scan_kernel(const GlobalParams p, const double* __restrict__ real, const double* aux1, const double* aux2,
-                       const double* packed, double* __restrict__ greal, double* extra, const long long* adam_step_dev,
-                       const int staged) {
+                       const double* packed, double* __restrict__ greal, double* extra, long long* adam_step_dev,
+                       const int do_update, const int staged) {
   pdl_enter();
   extern __shared__ double dyn[];
-  global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, staged, dyn);
+  global_bwd_scan_body(p, real, aux1, aux2, packed, greal, extra, adam_step_dev, do_update, staged, dyn);
 }
 
 // (3) element-parallel: chain to (m, log_s), loss = -elbo / Nsum, NaN scrub (global blocks only), Adam
@@ -463,7 +470,7 @@ global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const doubl
                    const double* __restrict__ packed, const double* __restrict__ scalars_in,
                    const double* __restrict__ greal, double* __restrict__ adam_m, double* __restrict__ adam_v,
                    double* __restrict__ grad_out, double* __restrict__ out_scalars,
-                   long long* step_dev, int* flag, int do_update, unsigned* ticket, const double* extra) {
+                   int* flag, int do_update, const double* extra) {
   pdl_enter();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -473,7 +480,7 @@ global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const doubl
   const double bc1 = extra[2 * CYTOF_MAX_K], bc2s = extra[2 * CYTOF_MAX_K + 1];   // from the backward scan
   auto adam = [&](int t, double g, bool scrub) {
     g *= p.grad_scale;
-    if (scrub && g != g) { g = 0.0; if (flag) *flag = 1; }
+    if (scrub && g != g) { g = 0.0; if (flag) *flag = 1; out_scalars[4] = 1.0; }   // same value from every writer
     if (grad_out) grad_out[t] = g;
     if (!do_update) return;
     const double mt = adam_m[t] + (1.0 - p.beta1) * (g - adam_m[t]);
@@ -505,12 +512,6 @@ global_adam_kernel(const GlobalParams p, double* __restrict__ theta, const doubl
     out_scalars[1] = ll;
     out_scalars[2] = lp;
     out_scalars[3] = lq;
-  }
-  // after ALL CTAs: out_scalars[4] = 1 if any NaN gradient was scrubbed in this step; bump the device step
-  // counter (every CTA read it at its start)
-  if (last_cta_done(ticket) && threadIdx.x == 0) {
-    out_scalars[4] = flag ? (double)*reinterpret_cast<volatile int*>(flag) : 0.0;
-    if (step_dev && do_update) *step_dev += 1;
   }
 }
 
@@ -634,24 +635,23 @@ int launch_global_bwd(const cytof_global_desc* g, double* theta, double* stash, 
   unsigned* tickets = reinterpret_cast<unsigned*>(stash + 5 * (size_t)R + 2 * kElemCtas);
   const BlockLayout blh = block_layout(p.I, p.J, p.K, p.L0, p.L1);
   double* extra = stash + 5 * (size_t)R + 2 * kElemCtas + 2;
-  const long long* sd = reinterpret_cast<const long long*>(step_dev);
+  long long* sd = reinterpret_cast<long long*>(step_dev);
   const size_t want = sizeof(double) * (2 * (size_t)R + (size_t)blh.total + 2);
   const size_t fused = scan_smem_bytes((const void*)global_bwd_elem_kernel, 1, want);
   const dim3 eg(kElemCtas), eb(kElemThreads);
   if (fused) {
     *err = launch_pdl(global_bwd_elem_kernel, eg, eb, fused, s, p, stash, stash + 3 * R, stash + 4 * R, packed,
-                      stash + 2 * R, flag, tickets + 1, extra, sd);
+                      stash + 2 * R, flag, tickets + 1, extra, sd, out_scalars, do_update);
   } else {
     *err = launch_pdl(global_bwd_elem_kernel, eg, eb, 0, s, p, stash, stash + 3 * R, stash + 4 * R, packed,
-                      stash + 2 * R, flag, nullptr, extra, sd);
+                      stash + 2 * R, flag, nullptr, extra, sd, out_scalars, do_update);
     if (*err == cudaSuccess)
       *err = launch_pdl(global_bwd_scan_kernel, dim3(1), dim3(1024), 0, s, p, stash, stash + 3 * R, stash + 4 * R, packed,
-                        stash + 2 * R, extra, sd, 0);
+                        stash + 2 * R, extra, sd, do_update, 0);
   }
   if (*err == cudaSuccess)
     *err = launch_pdl(global_adam_kernel, eg, eb, 0, s, p, theta, stash + R, packed, scalars_in, stash + 2 * R, adam_m,
-                      adam_v, grad_out, out_scalars, reinterpret_cast<long long*>(step_dev), flag, do_update, tickets + 2,
-                      extra);
+                      adam_v, grad_out, out_scalars, flag, do_update, extra);
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
 
