@@ -501,7 +501,7 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     return a;
   };
   auto sum_range = [&](int b0, int b1, int off) -> double {
-    // 4 independent loads in flight per lane, 8 lanes per output
+    // 4 independent loads in flight per lane, kFinLanes lanes (one warp) per output
     double a = 0.0;
     int b = b0 + sub;
     for (; b + 3 * kFinLanes < b1; b += 4 * kFinLanes) {
@@ -580,7 +580,7 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   const unsigned long long seq = peer.seq_dev ? (unsigned long long)(*peer.seq_dev + 1) : peer.seq;
   const int par = (int)(seq & 1ull);
   const size_t slot_off = kPeerHeaderBytes + ((size_t)par * peer.world + peer.rank) * (size_t)peer.nout * sizeof(double);
-  if (live) {     // the 8 lanes of an output share the peers between them
+  if (live) {     // the lanes of an output share the peers between them
     for (int q = sub; q < peer.world; q += kFinLanes)
       reinterpret_cast<double*>(peer.mailbox[q] + slot_off)[t] = r;
   }

@@ -577,7 +577,7 @@ int global_sizes(const cytof_global_desc* g, int64_t out[4]) {
   out[0] = p.roff[B_COUNT];                 // R: number of global reals (= noise length)
   out[1] = p.n_global;                      // 2R: scrubbed prefix of theta
   out[2] = p.n_global + 2 * p.I * p.J;      // P: length of theta
-  // stash: real | eps | greal | aux1 | aux2 | CTA partials | 3 tickets | cumprod(v) | its logit | Adam bias corrections
+  // stash: real | eps | greal | aux1 | aux2 | CTA partials | tickets (2 used) | cumprod(v) | its logit | Adam bias corrections
   out[3] = 5 * (int64_t)p.roff[B_COUNT] + 2 * kElemCtas + 2 + 2 * CYTOF_MAX_K + 2;
   return CYTOF_OK;
 }
