@@ -606,11 +606,22 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   __syncthreads();
   const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u;
   const double* slots = reinterpret_cast<const double*>(mine + kPeerHeaderBytes) + (size_t)par * peer.world * peer.nout;
-  for (int o = threadIdx.x; o < peer.nout; o += blockDim.x) {
-    double a = 0.0;
-    for (int q = 0; q < peer.world; ++q) a += __ldcg(slots + (size_t)q * peer.nout + o);
-    if (bad) a = __longlong_as_double(0x7ff8000000000000ll);
+  // one CTA sums world x nout doubles: all loads of two outputs (up to 32) are issued before the first add,
+  // otherwise this tail is a chain of L2 round trips; the sum runs in rank order on every rank (x + 0.0 = x)
+  for (int o = threadIdx.x; o < peer.nout; o += 2 * blockDim.x) {
+    const int o2 = o + blockDim.x;
+    double v[CYTOF_MAX_PEERS], w[CYTOF_MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < CYTOF_MAX_PEERS; ++q) {
+      v[q] = q < peer.world ? __ldcg(slots + (size_t)q * peer.nout + o) : 0.0;
+      w[q] = (q < peer.world && o2 < peer.nout) ? __ldcg(slots + (size_t)q * peer.nout + o2) : 0.0;
+    }
+    double a = 0.0, c = 0.0;
+#pragma unroll
+    for (int q = 0; q < CYTOF_MAX_PEERS; ++q) { a += v[q]; c += w[q]; }
+    if (bad) a = c = __longlong_as_double(0x7ff8000000000000ll);
     packed[o] = a;
+    if (o2 < peer.nout) packed[o2] = c;
   }
 }
 
