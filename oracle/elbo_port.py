@@ -84,10 +84,12 @@ def solve_beta(y_bounds, p_bounds):
     return np.linalg.solve(design, np.log(p) - np.log1p(-p))
 
 
-def prior_table(K, L0, L1):
-    """Priors of reference default_priors (Model.py:90-112), minus the sizes."""
+def prior_table(K, L0, L1, spec=None):
+    """Priors of reference default_priors (Model.py:90-112), minus the sizes; `spec`
+    ({key: [family, *hyper-parameters]}, the notation of oracle/gen_golden.py) replaces entries
+    the way a caller of the reference does (reference sims/cb/cb.py:117-123)."""
     one = lambda n: torch.ones(n, dtype=F64)
-    return {
+    tab = {
         'delta0': Gamma(torch.tensor(1., dtype=F64), torch.tensor(1., dtype=F64)),
         'delta1': Gamma(torch.tensor(1., dtype=F64), torch.tensor(1., dtype=F64)),
         'sig2': LogNormal(torch.tensor(-1., dtype=F64), torch.tensor(.1, dtype=F64)),
@@ -98,6 +100,15 @@ def prior_table(K, L0, L1):
         'W': Dirichlet(one(K) / K),
         'eps': Beta(torch.tensor(1., dtype=F64), torch.tensor(99., dtype=F64)),
     }
+    fam = {'Gamma': Gamma, 'Beta': Beta, 'LogNormal': LogNormal, 'Uniform': Uniform}
+    for k, (name, *args) in (spec or {}).items():
+        a = [torch.tensor(float(v), dtype=F64) for v in args]
+        if name == 'Dirichlet':       # one number c: Dirichlet(c * ones(n) / n)
+            n = tab[k].concentration.numel()
+            tab[k] = Dirichlet(a[0] * one(n) / n)
+        else:
+            tab[k] = fam[name](*a)
+    return tab
 
 
 def init_state(I, J, K, L0, L1, model_noisy=True, use_stick_break=True,
@@ -231,7 +242,7 @@ def elbo_port(state, y, idx, noise, cfg):
     returns dict(elbo, ll, lp, lq, log_qy) of 0-d fp64 tensors (graph attached)
     and 'y_imp' (list of imputed minibatches)."""
     keys = key_order(cfg['model_noisy'])
-    pri = prior_table(cfg['K'], cfg['L0'], cfg['L1'])
+    pri = prior_table(cfg['K'], cfg['L0'], cfg['L1'], cfg.get('prior_spec'))
     reals, params = {}, {}
     lq = 0.0
     for k in keys:
@@ -263,7 +274,7 @@ def elbo_port(state, y, idx, noise, cfg):
 
 
 def make_cfg(y, K, L0, L1, tau=0.1, use_stick_break=True, model_noisy=True, scale=1.0,
-             y_bounds=(-5., -3.5, -2.), p_bounds=(.05, .8, .05), noisy_var=10.0):
+             y_bounds=(-5., -3.5, -2.), p_bounds=(.05, .8, .05), noisy_var=10.0, prior_spec=None):
     I = len(y)
     beta = solve_beta(y_bounds, p_bounds)
     return {
@@ -273,6 +284,7 @@ def make_cfg(y, K, L0, L1, tau=0.1, use_stick_break=True, model_noisy=True, scal
         'scale': float(scale), 'noisy_sd': torch.sqrt(torch.tensor(noisy_var, dtype=F64)),
         'b0': torch.full((I,), beta[0], dtype=F64), 'b1': torch.full((I,), beta[1], dtype=F64),
         'b2': torch.full((I,), beta[2], dtype=F64),
+        'prior_spec': dict(prior_spec or {}),
     }
 
 

@@ -19,6 +19,7 @@ torch.distributions.Distribution.set_default_validate_args(False), needed on
 torch >= 1.8 because reference vae.py:29,33 builds Normal(., 0).
 """
 import copy
+import json
 import os
 import sys
 
@@ -73,10 +74,29 @@ def make_data(cytofpy, N, J, L0, L1, nan_frac_neg, seed):
     return y
 
 
+def apply_prior_spec(pri, spec):
+    """spec: {key: [family, *hyper-parameters]} -> torch distributions put into the reference's
+    priors dict the way reference sims/cb/cb.py:117-123 does.  A Dirichlet takes ONE number c and
+    means Dirichlet(c * ones(n) / n) with n the size of the default entry."""
+    import torch.distributions as D
+    for k, (fam, *args) in spec.items():
+        a = [torch.tensor(float(v), dtype=torch.float64) for v in args]
+        if fam == 'Dirichlet':
+            n = pri[k].concentration.numel()
+            pri[k] = D.Dirichlet(a[0] * torch.ones(n, dtype=torch.float64) / n)
+        elif fam == 'LogNormal':
+            pri[k] = D.LogNormal(*a)
+        else:
+            pri[k] = getattr(D, fam)(*a)
+    return pri
+
+
 def run_case(cytofpy, name, N, J, K, L0, L1, mb, tau, stick, noisy, scale,
-             nan_frac, train_steps=0, seed=0, traj=0):
+             nan_frac, train_steps=0, seed=0, traj=0, priors=None, train_lr=5e-2):
     y = make_data(cytofpy, N, J, L0, L1, nan_frac, seed)
     pri = cytofpy.model.default_priors(y, K=K, L=[L0, L1], y_bounds=[-5., -3.5, -2.])
+    if priors:
+        apply_prior_spec(pri, priors)
     torch.manual_seed(seed + 1)
     np.random.seed(seed + 1)
     mod = cytofpy.model.Model(y=y, priors=pri, tau=tau, verbose=-1, use_stick_break=stick,
@@ -87,13 +107,13 @@ def run_case(cytofpy, name, N, J, K, L0, L1, mb, tau, stick, noisy, scale,
         return [np.arange(n) if mb >= n else rng.choice(n, mb, replace=False) for n in N]
 
     if train_steps:
-        opt = torch.optim.Adam(mod.parameters(), lr=5e-2)
+        opt = torch.optim.Adam(mod.parameters(), lr=train_lr)
         for _ in range(train_steps):
             cytofpy.model.update(opt, mod, draw_idx())
 
     rec = {'meta_N': np.array(N), 'meta_J': J, 'meta_K': K, 'meta_L0': L0, 'meta_L1': L1,
            'meta_tau': tau, 'meta_stick': int(stick), 'meta_noisy': int(noisy),
-           'meta_scale': scale, 'meta_traj': traj}
+           'meta_scale': scale, 'meta_traj': traj, 'meta_priors': json.dumps(priors or {})}
     for i, yi in enumerate(y):
         rec['y_%d' % i] = yi.numpy()
     keys = list(mod.mp.keys())
@@ -172,6 +192,22 @@ CASES = [
          stick=False, noisy=False, scale=1.0, nan_frac=0.3, train_steps=100),
     dict(name='i_cfg4like_trained', N=[64, 64, 64, 64], J=32, K=30, L0=5, L1=5, mb=100000, tau=.1,
          stick=True, noisy=True, scale=1.0, nan_frac=0.0, train_steps=40),
+    # the cord-blood prior set of reference sims/cb/cb.py:115-123 (sig2 ~ Gamma(.1, 1)) at cfg3 shapes,
+    # trained to a mixed quiet / noisy state; gathered minibatch, NaN, no stick-breaking, tau = .001
+    dict(name='j_cb_priors_cfg3', N=[96, 64, 80], J=32, K=30, L0=5, L1=3, mb=48, tau=.001,
+         stick=False, noisy=True, scale=0.1, nan_frac=0.3, train_steps=1500, seed=4, train_lr=0.05,
+         priors={'sig2': ['Gamma', .1, 1.], 'alpha': ['Gamma', .1, .1], 'delta0': ['Gamma', 1., 1.],
+                 'delta1': ['Gamma', 1., 1.], 'eps': ['Beta', 1., 99.]}),
+    # non-default hyper-parameters of every recognised family at cfg1 shapes (K = 5, L = 3/3, full batch)
+    dict(name='k_priors_cfg1', N=[120, 80, 100], J=32, K=5, L0=3, L1=3, mb=100000, tau=.1,
+         stick=True, noisy=True, scale=1.0, nan_frac=0.2, train_steps=400, seed=5,
+         priors={'sig2': ['Gamma', .5, 2.], 'alpha': ['Gamma', 2., .1], 'delta0': ['Gamma', 2., .5],
+                 'delta1': ['Gamma', 1.5, 2.], 'eps': ['Beta', 2., 50.], 'eta0': ['Dirichlet', 2.1],
+                 'eta1': ['Dirichlet', .6], 'W': ['Dirichlet', 3.5]}),
+    # trained mixed state at cfg2 shapes (J = 32, K = 30, L = 5/3) with the LogNormal sig2 prior moved
+    dict(name='l_cfg2_trained_mixed', N=[96, 64, 80], J=32, K=30, L0=5, L1=3, mb=48, tau=.1,
+         stick=True, noisy=True, scale=1.0, nan_frac=0.0, train_steps=150, seed=6,
+         priors={'sig2': ['LogNormal', -.5, .3]}),
     dict(name='t_traj3', N=[300, 100, 200], J=8, K=10, L0=3, L1=3, mb=100, tau=.1,
          stick=True, noisy=True, scale=1.0, nan_frac=0.3, traj=3),
 ]
@@ -179,8 +215,10 @@ CASES = [
 
 def main():
     cytofpy = _import_reference()
+    only = sys.argv[1:]
     for c in CASES:
-        run_case(cytofpy, **c)
+        if not only or c['name'] in only:
+            run_case(cytofpy, **c)
 
 
 if __name__ == '__main__':

@@ -2,6 +2,7 @@
 by oracle/gen_golden.py from the live reference) into the plain-dict form the
 oracle port and the product both understand."""
 import glob
+import json
 import os
 
 import numpy as np
@@ -32,11 +33,14 @@ class Case:
         self.scale = float(z['meta_scale'])
         self.keys = [str(k) for k in z['meta_keys']]
         self.traj = int(z['meta_traj'])
+        # prior overrides in the notation of oracle/gen_golden.py ({} = reference default_priors)
+        self.prior_spec = json.loads(str(z['meta_priors'])) if 'meta_priors' in z.files else {}
         self.y = [torch.tensor(z['y_%d' % i], dtype=F64) for i in range(self.I)]
 
     def cfg(self):
         return port.make_cfg(self.y, self.K, self.L0, self.L1, tau=self.tau,
-                             use_stick_break=self.stick, model_noisy=self.noisy, scale=self.scale)
+                             use_stick_break=self.stick, model_noisy=self.noisy, scale=self.scale,
+                             prior_spec=self.prior_spec)
 
     def state(self):
         st = {k: torch.tensor(self.z['vp_' + k], dtype=F64, requires_grad=True) for k in self.keys}

@@ -28,9 +28,24 @@ def replay_noise(tensors, target):
         tdn._standard_normal = orig
 
 
+def apply_prior_spec(pri, spec):
+    """Replace entries of a priors dict the way reference sims/cb/cb.py:117-123 does; `spec` is the
+    {key: [family, *hyper-parameters]} record of a golden fixture (oracle/gen_golden.py)."""
+    import torch.distributions as D
+    for k, (fam, *args) in spec.items():
+        a = [torch.tensor(float(v), dtype=F64) for v in args]
+        if fam == 'Dirichlet':
+            n = pri[k].concentration.numel()
+            pri[k] = D.Dirichlet(a[0] * torch.ones(n, dtype=F64) / n)
+        else:
+            pri[k] = getattr(D, fam)(*a)
+    return pri
+
+
 def build_model(case, device, engine_factory=None, noise='external'):
     y = [t.clone() for t in case.y]
     pri = cy.model.default_priors(y, K=case.K, L=[case.L0, case.L1], y_bounds=[-5., -3.5, -2.])
+    apply_prior_spec(pri, getattr(case, 'prior_spec', {}))
     mod = cy.model.Model(y=y, priors=pri, tau=case.tau, verbose=-1, use_stick_break=case.stick,
                          model_noisy=case.noisy, scale=case.scale, device=device, noise=noise,
                          _engine_factory=engine_factory)

@@ -395,3 +395,54 @@ def test_full_size_properties_cfg5_shape():
     bb, l2 = eng.fwdbwd(Batch([150] * I, it, None, step=1), G, zm)
     assert abs(l2[0].item() - ll_ref) <= ELBO_TOL * abs(ll_ref)
     check_block(bb.cpu().numpy().astype(np.float64), blk_ref, lay)
+
+
+def _oracle_whole_matrix(y64, N, g, model_noisy, noisy_sd, eps=None, scale=1.0):
+    """fp64 C oracle (oracle/cells_oracle.c) over EVERY cell of every sample, one thread per sample
+    (ctypes drops the GIL); the gradient block and ll are additive over samples."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cells_c
+    cells_c.build()
+    I = len(N)
+    row_base = np.concatenate([[0], np.cumsum(N)])[:-1]
+    y_all = np.concatenate(y64, 0)
+
+    def one(i):
+        counts = [N[q] if q == i else 0 for q in range(I)]
+        e = None if eps is None else eps[i]
+        return cells_c.cells_fwdbwd_c(y_all, row_base, counts, None, e, g, np.ones(I), scale, noisy_sd, model_noisy)
+
+    with ThreadPoolExecutor(max_workers=min(I, 16)) as pool:
+        parts = list(pool.map(one, range(I)))
+    return sum(p[0] for p in parts), sum(p[1] for p in parts), sum(p[2] for p in parts)
+
+
+@pytest.mark.parametrize('noisy', [True, False])
+def test_full_size_fp64_oracle_cfg4(noisy):
+    """BASELINE cfg4 at FULL size — I = 8 x 125,000 cells, J = 32, K = 30, L = 5/5, one kernel launch
+    over the whole 1 M-cell matrix — against the fp64 oracle evaluated over the same 1 M cells
+    (SURVEY H2-iii): ll within 1e-5, every section of the gradient block within 1e-4.  noisy=False is
+    the rho == 1 regime (every likelihood gradient at full weight); noisy=True uses a state whose
+    quiet / noisy responsibilities are mixed."""
+    I, J, K, L0, L1 = 8, 32, 30, 5, 5
+    N = [125000] * I
+    dev = _dev()
+    s = cy.util.synth_cytof(N, J, [100.] * 5, L0, L1, seed=0)
+    _, g = _random_problem(I, J, K, L0, L1, [1] * I, 0.0, seed=31)
+    g['mu0'], g['mu1'] = -(np.arange(L0) + 1.5), np.arange(L1) + 1.5
+    # sig, eps and the sd of the noisy class are chosen so that the quiet share sum_n rho / N_i of the
+    # samples lies between 0.07 and 0.87 (bisection with the oracle on a slice): a genuinely mixed state
+    g['sig'], g['eps'], noisy_sd = np.linspace(1.25, 1.35, I), np.full(I, 0.01), 1.8
+    y64 = [a.astype(np.float64) for a in s['y']]
+    ll_ref, _, blk_ref = _oracle_whole_matrix(y64, N, g, noisy, noisy_sd)
+    eng = CellEngine([torch.from_numpy(a) for a in s['y']], dev, K, L0, L1, noisy, noisy_sd, 1.0, g['b'], seed=9)
+    G, zm = pack_globals(g, I, noisy).to(dev), pack_zmask(g['Z']).to(dev)
+    blk, ll = eng.fwdbwd(Batch(N, None, None, step=1), G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy().copy()
+    lay = ccf.block_layout(I, J, K, L0, L1)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref), (ll[0], ll_ref)
+    if noisy:     # the state must actually be mixed, otherwise this case tests nothing beyond noisy=False
+        dl = blk_ref[lay['dlogW'][0]:lay['dlogW'][0] + lay['dlogW'][1]].reshape(I, K).sum(1)   # sum_n fac rho
+        frac = dl / np.array(N)
+        assert (frac > 0.02).all() and (frac < 0.98).all(), frac
+    check_block(blk, blk_ref, lay)

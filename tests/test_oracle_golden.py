@@ -126,8 +126,9 @@ def _torch_cells(t, rows, eps, fac, cfg, b):
 @pytest.mark.skipif(not __import__('os').path.isdir('/root/reference/cytofpy'),
                     reason='needs the live reference (build container only)')
 def test_lam_post_port_matches_reference():
-    """oracle/lam_post_port.py vs the live reference post_proc (probabilities recomputed from the
-    reference's own formulas, lam_post.py:20-51, on a sample_params.theta draw)."""
+    """oracle/lam_post_port.py vs the probabilities the live reference hands to its own sampler:
+    `Categorical` inside cytofpy.model.post_proc.lam_post is replaced by a recorder, so the
+    captured tensors ARE the `lam_probs` of reference lam_post.py:51-53 (no restated formula)."""
     import subprocess
     import sys
     code = r'''
@@ -135,7 +136,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r)
 torch.distributions.Distribution.set_default_validate_args(False)
 import cytofpy
-from torch.distributions import Normal
+from cytofpy.model.post_proc import lam_post as ref_lam_post
 from oracle import lam_post_port
 torch.manual_seed(0); np.random.seed(0)
 y = cytofpy.util.simdata(N=[60, 40], J=6, a_W=[100.]*3, L0=3, L1=2)['data']['y']
@@ -143,20 +144,21 @@ y[0][0, 1] = float('nan')
 pri = cytofpy.model.default_priors(y, K=4, L=[3, 2], y_bounds=[-5., -3.5, -2.])
 mod = cytofpy.model.Model(y=y, priors=pri, verbose=-1)
 th, _ = cytofpy.model.post_proc.sample_params.theta(mod, pri)
-ref = []
-for i in range(mod.I):
-    yi, e, W = th['y'][i], th['eps'][i], th['W'][i]
-    lp0 = e.log() + Normal(0, th['noisy_sd']).log_prob(yi).sum(1, keepdim=True)
-    a0 = Normal(th['mu0'][None, None, :], th['sig'][i]).log_prob(yi[:, :, None]) + th['eta0'][i:i+1].log()
-    a1 = Normal(th['mu1'][None, None, :], th['sig'][i]).log_prob(yi[:, :, None]) + th['eta1'][i:i+1].log()
-    m0, m1 = a0.logsumexp(2), a1.logsumexp(2)
-    f = (th['Z'][None] * m1[:, :, None] + (1 - th['Z'][None]) * m0[:, :, None]).sum(1)
-    lp = torch.cat((lp0, torch.log1p(-e) + W.log()[None] + f), 1)
-    ref.append((lp - lp.logsumexp(1, keepdim=True)).exp().numpy())
+captured = []
+real_categorical = ref_lam_post.Categorical
+class Recorder(real_categorical):
+    def __init__(self, probs=None, **kw):
+        captured.append(probs.detach().clone().numpy())
+        super().__init__(probs, **kw)
+ref_lam_post.Categorical = Recorder
+lam = ref_lam_post.sample(th, mod)
+ref_lam_post.Categorical = real_categorical
+assert len(captured) == mod.I and all(c.shape == (n, 5) for c, n in zip(captured, [60, 40]))
+assert all(int(l.max()) <= 4 for l in lam)
 tn = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in th.items() if k != 'y'}
 tn['noisy_sd'] = float(th['noisy_sd']); tn['y'] = [t.numpy() for t in th['y']]
 got = lam_post_port.label_probs(tn)
-print(max(float(np.abs(a - b).max()) for a, b in zip(got, ref)))
+print(max(float(np.abs(a - b).max()) for a, b in zip(got, captured)))
 ''' % ROOT_DIR
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
