@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200.so')
 # same sources with the dZ accumulation on tcgen05.mma + TMEM (csrc/elbo_kernel_mma.cuh, CYTOF_TMEM_DZ):
 # measured 5 % slower than the default at cfg4, kept as a tested variant (tests/test_gpu_tmem_variant.py)
 TMEM_LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200_tmem.so')
-SOURCES = ['variants_mma64.cu', 'variants_mma.cu', 'elbo_kernel.cu', 'global_part.cu', 'labels.cu', 'abi.cu']
+SOURCES = ['variants_mma64.cu', 'variants_mma.cu', 'variants_umma.cu', 'elbo_kernel.cu', 'global_part.cu', 'labels.cu', 'abi.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC']
 

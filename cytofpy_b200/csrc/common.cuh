@@ -88,6 +88,9 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
 // keyed by (global row / 4, marker) and yields FOUR normals (two Box-Muller pairs), one for each
 // of the 4 consecutive rows of the group: a warp that walks consecutive rows (full-batch tiles)
 // pays one Philox block per 4 cells.  Independent of how cells are split over warps, CTAs or GPUs.
+// Third counter word of the per-cell draws: marker | sample << 8, so that row r of different samples (every sample's
+// rows start at row_global[i], often 0) gets independent draws, as the reference's dense normal_ does (vae.py:33).
+__device__ __forceinline__ uint32_t philox_ctr(int j, int sample) { return (uint32_t)j | ((uint32_t)sample << 8); }
 __device__ __forceinline__ float philox_unit(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uint64_t grp, uint32_t j, float out[4]) {
   uint32_t c[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), j, step};
@@ -209,6 +212,10 @@ using KernelFn = void (*)(const ElboParams);
 KernelFn mma_kernel_fn(int lidx, int fi);
 // lidx: 0 = (5,5), 1 = (8,8); missing: imputation path compiled in; fi = noisy + 2 * has_idx + 4 * (tail passes - 1)
 KernelFn mma64_kernel_fn(int lidx, int missing, int fi);
+// CTA-wide tcgen05 kernel (elbo_kernel_umma.cuh): lidx 0 = (3,3), 1 = (5,3), 2 = (5,5); fi as for mma_kernel_fn
+KernelFn umma_kernel_fn(int lidx, int fi);
+int umma_smem_bytes();
+int umma_threads();
 
 __device__ __forceinline__ uint32_t elbo_step(const ElboParams& p) {
   return p.step_dev ? (uint32_t)(*p.step_dev + 1) : p.step;

@@ -200,7 +200,7 @@ elbo_fwdbwd_kernel(const ElboParams p) {
           const int j = lane + 32 * jp;
           e[jp] = p.noise_mode == CYTOF_NOISE_EXTERNAL
                       ? (p.eps ? __ldg(p.eps + (cb + c) * J + j) : 0.f)
-                      : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)(row_cur - row_base), j);
+                      : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)(row_cur - row_base), philox_ctr(j, i));
           yv[jp] = fmaf(sd[jp], e[jp], vm[jp]);
         }
     }
@@ -640,7 +640,7 @@ __global__ void impute_emit_kernel(const ElboParams p, float* __restrict__ eps_o
   if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
     if (p.eps) e = p.eps[c * p.J + j];
   } else {
-    e = philox_normal(p.seed, elbo_step(p), (unsigned long long)(p.row_global[i] + lrow), j);
+    e = philox_normal(p.seed, elbo_step(p), (unsigned long long)(p.row_global[i] + lrow), philox_ctr(j, i));
   }
   if (eps_out) { eps_out[t] = e; return; }
   const GlobalsLayout gl = globals_layout(p.I, p.J, p.K, p.L0, p.L1);
@@ -658,6 +658,7 @@ struct Variant {
   KernelFn fn[8];  // [noisy + 2 * has_idx + 4 * no_missing] (the last bit only selects a different kernel in the MMA variants)
   bool records_alias;   // the final per-warp records reuse the main-loop shared memory
   int threads;          // CTA size (0 = kThreads)
+  int smem_bytes;       // fixed dynamic shared memory size (0 = derived from the per-warp figures)
 };
 static int variant_threads(const Variant* v) { return v->threads ? v->threads : kThreads; }
 #define CYTOF_VARIANT(a, b, jp, kp) \
@@ -721,6 +722,24 @@ static const Variant* pick_variant64(const cytof_desc* d) {
   return nullptr;
 }
 
+// J, K <= 32 with 16-byte rows: the CTA-wide tcgen05 kernel (elbo_kernel_umma.cuh), selected with CYTOF_UMMA=1 in the
+// environment.  Parity-green (tests/test_gpu_umma_variant.py) but MEASURED SLOWER than the per-warp mma.sync kernel at
+// cfg4 (0.486 vs 0.269 ms per 1 M cells; profiles/README.md "round 2": TMEM reads run at 32 B/clk/SM, SS-mode MMAs
+// stream their operands from shared memory at 128 B/clk, and the forward -> backward round trip through two
+// single-thread issuers and the cell warps is ~5,000 cycles), so it is not the default.
+#define CYTOF_VARIANT_UMMA(a, b, lidx) { a, b, 1, 1, 0, 0, CYTOF_FN8(umma_kernel_fn, lidx), true, 512, -1 }
+static const Variant kVariantsU[] = { CYTOF_VARIANT_UMMA(3, 3, 0), CYTOF_VARIANT_UMMA(5, 3, 1), CYTOF_VARIANT_UMMA(5, 5, 2) };
+static bool umma_enabled() {
+  static const bool on = [] { const char* e = getenv("CYTOF_UMMA"); return e && e[0] == '1'; }();
+  return on;
+}
+static const Variant* pick_variant_umma(const cytof_desc* d, const float* y) {
+  if (!umma_enabled() || d->J > 32 || (d->J & 3) || d->K > 32 || (reinterpret_cast<uintptr_t>(y) & 15)) return nullptr;
+  for (const Variant& v : kVariantsU)
+    if (v.lm0 >= d->L0 && v.lm1 >= d->L1) return &v;
+  return nullptr;
+}
+
 static const Variant* pick_variant(int J, int K, int L0, int L1) {
   const int jp = J <= 32 ? 1 : 2, kp = K <= 32 ? 1 : 2;
   const int need = jp > kp ? jp : kp;
@@ -730,6 +749,7 @@ static const Variant* pick_variant(int J, int K, int L0, int L1) {
 }
 
 static size_t fused_smem_bytes(const Variant* v, int J, int K, int L0, int L1) {
+  if (v->smem_bytes) return (size_t)umma_smem_bytes();
   const PartialLayout pl = partial_layout(J, K, L0, L1);
   // the J,K<=32 kernel keeps one partial record per warp in shared memory for its final reduction
   const size_t nwarps = variant_threads(v) / 32;
@@ -759,12 +779,13 @@ int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAM
 // resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached per
 // device; re-evaluated when a different problem shape changes the shared-memory footprint)
 struct OccEntry { size_t smem, smem_attr; int occ; };
-static OccEntry g_occ[64][20][8] = {};
+static OccEntry g_occ[64][24][8] = {};
 static int variant_occupancy(const Variant* v, int fi, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
   const bool is64 = v >= kVariants64 && v < kVariants64 + 4;
-  OccEntry& e = g_occ[dev][is64 ? 16 + (int)(v - kVariants64) : (int)(v - kVariants)][fi];
+  const bool isu = v >= kVariantsU && v < kVariantsU + 3;
+  OccEntry& e = g_occ[dev][isu ? 20 + (int)(v - kVariantsU) : is64 ? 16 + (int)(v - kVariants64) : (int)(v - kVariants)][fi];
   if (e.occ == 0 || e.smem != smem) {
     if (smem > 48 * 1024 && smem > e.smem_attr) {   // opt in to large dynamic shared memory
       cudaFuncSetAttribute(v->fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -861,7 +882,8 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
                   double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
                   cudaError_t* err, const cytof_peer_desc* peer) {
   const Variant* v64 = pick_variant64(d);
-  const Variant* v = v64 ? v64 : pick_variant(d->J, d->K, d->L0, d->L1);
+  const Variant* vu = v64 ? nullptr : pick_variant_umma(d, y);
+  const Variant* v = v64 ? v64 : (vu ? vu : pick_variant(d->J, d->K, d->L0, d->L1));
   ElboParams p;
   fill_params(d, &p);
   p.y = y; p.idx = idx; p.eps = eps; p.globals = globals;

@@ -232,7 +232,7 @@ elbo_fwdbwd_j32_kernel(const ElboParams p) {
       if (anym[u] && miss[u]) {
         e[u] = p.noise_mode == CYTOF_NOISE_EXTERNAL
                    ? (p.eps ? __ldg(p.eps + (cb + c_lo + t + u) * J + lane) : 0.f)
-                   : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)row_cur[u], lane);
+                   : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)row_cur[u], philox_ctr(lane, i));
         yv[u] = fmaf(sd, e[u], vm);
       }
     }

@@ -374,7 +374,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
         const unsigned gm = (u0 >= 0 ? (0xfu << u0) : (0xfu >> -u0)) & 0xffu;
         if (!(amask & gm)) continue;             // warp-uniform: no cell of this block misses anything
         float nz[4];
-        philox_normal4(p.seed, elbo_step(p), grp0 + (unsigned long long)gi, lane, nz);
+        philox_normal4(p.seed, elbo_step(p), grp0 + (unsigned long long)gi, philox_ctr(lane, i), nz);
 #pragma unroll
         for (int w = 0; w < 4; ++w) sW[(4 * gi + w) * 32 + lane] = nz[w];
       }
@@ -396,7 +396,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
           const unsigned long long grow = grow_base + (unsigned long long)row;
           if ((grow >> 2) != grp_c) {            // warp-uniform
             grp_c = grow >> 2;
-            philox_normal4(p.seed, elbo_step(p), grp_c, lane, nz);
+            philox_normal4(p.seed, elbo_step(p), grp_c, philox_ctr(lane, i), nz);
           }
           const unsigned w = (unsigned)grow & 3u;
           e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));

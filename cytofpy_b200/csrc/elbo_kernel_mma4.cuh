@@ -215,7 +215,7 @@ elbo_fwdbwd_mma4_kernel(const ElboParams p) {
           const unsigned long long grow = grow_base + (unsigned long long)row;
           if ((grow >> 2) != grp_c) {            // warp-uniform
             grp_c = grow >> 2;
-            philox_normal4(p.seed, elbo_step(p), grp_c, lane, nz);
+            philox_normal4(p.seed, elbo_step(p), grp_c, philox_ctr(lane, i), nz);
           }
           const unsigned w = (unsigned)grow & 3u;
           e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));

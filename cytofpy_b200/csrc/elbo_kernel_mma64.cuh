@@ -327,7 +327,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
           const unsigned long long grow = grow_base + (unsigned long long)row;
           if ((grow >> 2) != grp_c) {
             grp_c = grow >> 2;
-            philox_normal4(p.seed, elbo_step(p), grp_c, lane, nz);
+            philox_normal4(p.seed, elbo_step(p), grp_c, philox_ctr(lane, i), nz);
           }
           const unsigned w = (unsigned)grow & 3u;
           e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));
@@ -342,7 +342,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
           const int row = HAS_IDX ? __ldg(idx + tn + cu) : first_row + tn + cu;
           src[cu * kXJS + jt] = p.noise_mode == CYTOF_NOISE_EXTERNAL
                                     ? (p.eps ? __ldg(p.eps + (cb + c_lo + tn + cu) * J + jt) : 0.f)
-                                    : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)row, jt);
+                                    : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)row, philox_ctr(jt, i));
         }
       }
     }

@@ -23,10 +23,12 @@ def main():
     ap.add_argument('--workload', default='cfg4')
     ap.add_argument('--nan', type=float, default=0.0)
     ap.add_argument('--mb', type=int, default=0)
+    ap.add_argument('--n', type=int, default=0, help='cells per sample (overrides the workload)')
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--force-missing', action='store_true', help='kernels with the imputation path even for clean data')
     a = ap.parse_args()
     I, n, J, K, L0, L1 = SH[a.workload]
+    n = a.n or n
     dev = torch.device('cuda', 0)
     rng = np.random.default_rng(0)
     g = torch.Generator(device=dev).manual_seed(0)
