@@ -20,9 +20,7 @@
 #include <string.h>
 
 #include "common.cuh"
-#include "elbo_kernel_j32.cuh"
 #include "elbo_kernel_mma.cuh"
-#include "elbo_kernel_mma4.cuh"
 #include "elbo_kernel_mma64.cuh"
 
 namespace cytof {
@@ -666,36 +664,17 @@ static int variant_threads(const Variant* v) { return v->threads ? v->threads : 
                                            elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
                                            elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
                                            elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true> } }
-#define CYTOF_VARIANT_J32(a, b) \
-  { a, b, 1, 1, kCPW * 64, kJ32ConstFloats, { elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
-                             elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true>, \
-                             elbo_fwdbwd_j32_kernel<a, b, false, false>, elbo_fwdbwd_j32_kernel<a, b, true, false>, \
-                             elbo_fwdbwd_j32_kernel<a, b, false, true>, elbo_fwdbwd_j32_kernel<a, b, true, true> } }
 #define CYTOF_FN8(f, ...) { f(__VA_ARGS__, 0), f(__VA_ARGS__, 1), f(__VA_ARGS__, 2), f(__VA_ARGS__, 3), \
                             f(__VA_ARGS__, 4), f(__VA_ARGS__, 5), f(__VA_ARGS__, 6), f(__VA_ARGS__, 7) }
 #define CYTOF_VARIANT_MMA(a, b, lidx) \
   { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, CYTOF_FN8(mma_kernel_fn, lidx), true }
-#define CYTOF_VARIANT_MMA4(a, b) \
-  { a, b, 1, 1, kQWarpFloats, kMmaZFloats, { elbo_fwdbwd_mma4_kernel<a, b, false, false, true>, elbo_fwdbwd_mma4_kernel<a, b, true, false, true>, \
-                             elbo_fwdbwd_mma4_kernel<a, b, false, true, true>, elbo_fwdbwd_mma4_kernel<a, b, true, true, true>, \
-                             elbo_fwdbwd_mma4_kernel<a, b, false, false, false>, elbo_fwdbwd_mma4_kernel<a, b, true, false, false>, \
-                             elbo_fwdbwd_mma4_kernel<a, b, false, true, false>, elbo_fwdbwd_mma4_kernel<a, b, true, true, false> }, true, kQThreads }
 #ifndef CYTOF_MMA
-#define CYTOF_MMA 1   // 1: tensor-core kernel, 8 cells per warp iteration, 8 warps/SM (fastest measured);
-                      // 2: 4 cells per iteration, 12 warps/SM (elbo_kernel_mma4.cuh: issue 56 % but +28 % instructions)
-#endif
-#ifndef CYTOF_J32
-#define CYTOF_J32 1   // 1: packed-fp32, two-cells-in-flight kernel for J,K <= 32; 0: first kernel
+#define CYTOF_MMA 1   // 1: tensor-core kernel (elbo_kernel_mma.cuh) for J, K <= 32; 0: the first SIMT kernel (A/B builds)
 #endif
 // ordered by cost: the first variant that fits is used; (8,8) is the padded fallback
 static const Variant kVariants[] = {
-#if CYTOF_MMA == 2
-    CYTOF_VARIANT_MMA4(3, 3), CYTOF_VARIANT_MMA4(5, 3), CYTOF_VARIANT_MMA4(5, 5), CYTOF_VARIANT_MMA4(8, 8),
-#elif CYTOF_MMA
+#if CYTOF_MMA
     CYTOF_VARIANT_MMA(3, 3, 0), CYTOF_VARIANT_MMA(5, 3, 1), CYTOF_VARIANT_MMA(5, 5, 2), CYTOF_VARIANT_MMA(8, 8, 3),
-#elif CYTOF_J32
-    CYTOF_VARIANT_J32(3, 3), CYTOF_VARIANT_J32(4, 3), CYTOF_VARIANT_J32(5, 3),
-    CYTOF_VARIANT_J32(5, 5), CYTOF_VARIANT_J32(8, 8),
 #else
     CYTOF_VARIANT(3, 3, 1, 1), CYTOF_VARIANT(4, 3, 1, 1), CYTOF_VARIANT(5, 3, 1, 1),
     CYTOF_VARIANT(5, 5, 1, 1), CYTOF_VARIANT(8, 8, 1, 1),

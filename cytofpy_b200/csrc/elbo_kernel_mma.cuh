@@ -22,7 +22,7 @@
 // first MMA (thread (g,t) owns cells 2t, 2t+1 and features g, g+8, g+16, g+24).
 #pragma once
 #include <cstdio>
-#include "elbo_kernel_j32.cuh"
+#include "common.cuh"
 
 namespace cytof {
 
@@ -40,8 +40,8 @@ constexpr int kMmaZFloats = 2 * 8 * 32 * 4 + kMmaHdrFloats;     // A-fragment ta
 
 
 // Packed fp32 through the CUDA 12.9 sm_100 intrinsics (FFMA2 / FADD2 / FMUL2 on float2): unlike
-// the inline-PTX pairs of elbo_kernel_j32.cuh the compiler sees the two halves, so no MOVs are
-// spent on packing and unpacking register pairs.
+// inline-PTX f32x2 pairs the compiler sees the two halves, so no MOVs are spent on packing and
+// unpacking register pairs.
 __device__ __forceinline__ float2 mkp(float lo, float hi) { return make_float2(lo, hi); }
 __device__ __forceinline__ float2 bcp(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float lo2(float2 a) { return a.x; }

@@ -19,7 +19,7 @@
 //     the epilogue reads the accumulator with tcgen05.ld.  (-DCYTOF_X_TMEM=0: the same with mma.sync,
 //     warp w accumulating n-tile w over the tiles of all warps -- 5 % slower.)
 #pragma once
-#include "elbo_kernel_mma4.cuh"
+#include "elbo_kernel_mma.cuh"
 
 namespace cytof {
 

@@ -56,7 +56,7 @@ class _CellELBO(torch.autograd.Function):
 class Model(torch.nn.Module):
     def __init__(self, y, priors, m=None, y_mean_init=-3.0, y_sd_init=0.1, tau=0.1, verbose=1,
                  use_stick_break=True, model_noisy=True, scale=1, device=None, noise='philox',
-                 seed=0, N_global=None, row_global=None, dist_group=None, _engine_factory=None):
+                 seed=0, N_global=None, row_global=None, dist_group=None):
         """Arguments up to `scale` are the reference's (Model.py:115-116).  Extra, all optional:
         device (default cuda:current), noise ('philox' in-kernel draws | 'external' torch
         draws, used by the parity tests), seed (Philox key), and for cell-sharded multi-GPU
@@ -108,11 +108,11 @@ class Model(torch.nn.Module):
         mp['alpha'] = ModelParam(1, 'positive', device=dev)
         mp['v'] = ModelParam(K, 'unit_interval', ones(K) * .99 if use_stick_break else None, device=dev)
         mp['H'] = ModelParam((J, K), 'unit_interval', device=dev)
-        self.mp = mp
+        self._mp = mp
         for key, p in mp.items():
             setattr(self, key + '_vp', p.vp)
-        self.y_vae = [VAE(J, mean_init=y_mean_init, sd_init=y_sd_init, device=dev) for _ in range(I)]
-        self.y_vae_vp = ParameterList([q for vae in self.y_vae for q in vae.parameters()])
+        self._y_vae = [VAE(J, mean_init=y_mean_init, sd_init=y_sd_init, device=dev) for _ in range(I)]
+        self.y_vae_vp = ParameterList([q for vae in self._y_vae for q in vae.parameters()])
 
         # device-resident data + C-ABI engine (masks given separately are folded into NaN)
         y_eff = []
@@ -122,10 +122,40 @@ class Model(torch.nn.Module):
             y_eff.append(t)
         b = torch.stack([torch.as_tensor(self.b0, dtype=F64), torch.as_tensor(self.b1, dtype=F64),
                          torch.as_tensor(self.b2, dtype=F64)], 1)
-        make = CellEngine if _engine_factory is None else _engine_factory   # tests inject a stub
-        self.engine = make(y_eff, dev, K, L[0], L[1], model_noisy, float(self.noisy_sd),
-                           float(scale), b, N_global=N_global, row_global=row_global, seed=seed)
+        self.engine = self._make_engine(y_eff, dev, K, L[0], L[1], model_noisy, float(self.noisy_sd),
+                                        float(scale), b, N_global=N_global, row_global=row_global, seed=seed)
         self.N_local = self.engine.N_local
+
+    # `mod.mp = out['mp']; mod.y_vae = out['vae']` is how the reference's callers restore a fitted model
+    # (sims/cb/cb.py:173-179).  Here the registered parameters (and the fused step's flat buffer they
+    # may be views of) stay in place on the device and the assigned values are copied into them.
+    @property
+    def mp(self):
+        return self._mp
+
+    @mp.setter
+    def mp(self, new):
+        with torch.no_grad():
+            for key, p in self._mp.items():
+                p.vp.copy_(new[key].vp.to(device=p.vp.device, dtype=p.vp.dtype))
+
+    @property
+    def y_vae(self):
+        return self._y_vae
+
+    @y_vae.setter
+    def y_vae(self, new):
+        if len(new) != len(self._y_vae):
+            raise ValueError('y_vae: expected %d samples, got %d' % (len(self._y_vae), len(new)))
+        with torch.no_grad():
+            for mine, theirs in zip(self._y_vae, new):
+                mine.mean.copy_(theirs.mean.to(device=mine.mean.device, dtype=mine.mean.dtype))
+                mine.log_sd.copy_(theirs.log_sd.to(device=mine.log_sd.device, dtype=mine.log_sd.dtype))
+
+    def _make_engine(self, *args, **kwargs):
+        """The per-cell engine: always the CUDA one (no CPU fallback; CellEngine raises without the
+        library or a CUDA device).  The CPU-only host-logic tests subclass Model under tests/."""
+        return CellEngine(*args, **kwargs)
 
     # ------------------------------------------------------------------ batches
     def _counts_global(self, batch):

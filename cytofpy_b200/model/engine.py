@@ -101,18 +101,29 @@ class CellEngine:
         counts = [len(ix) for ix in idx_list]
         if all(isinstance(ix, range) and ix == range(n) for ix, n in zip(idx_list, self.N_local)):
             return counts, None
-        if not any(torch.is_tensor(ix) for ix in idx_list):
-            host = np.concatenate([np.asarray(ix, dtype=np.int32).reshape(-1) for ix in idx_list]) \
-                if sum(counts) else np.zeros(0, np.int32)
+        # host-side indices are range-checked like the reference's y[idx] (IndexError; negative values
+        # wrap once, numpy style): the kernel's row gather itself is unchecked
+        host_parts = {}
+        for q, (ix, n) in enumerate(zip(idx_list, self.N_local)):
+            if torch.is_tensor(ix) and ix.is_cuda:
+                continue
+            a = np.asarray(ix.cpu() if torch.is_tensor(ix) else ix).reshape(-1)
+            if a.size:
+                if not np.issubdtype(a.dtype, np.integer):
+                    raise IndexError('cytofpy_b200: minibatch indices must be integers')
+                a = np.where(a < 0, a + n, a)
+                if a.min() < 0 or a.max() >= n:
+                    raise IndexError('cytofpy_b200: index out of range for sample %d with %d cells' % (q, n))
+            host_parts[q] = a.astype(np.int32)
+        if len(host_parts) == len(idx_list):
+            host = np.concatenate([host_parts[q] for q in range(len(idx_list))]) if sum(counts) else np.zeros(0, np.int32)
             return counts, torch.from_numpy(host).to(self.device, non_blocking=True)
         parts = []
-        for ix in idx_list:
-            if torch.is_tensor(ix):
-                parts.append(ix.to(device=self.device, dtype=torch.int32))
-            elif isinstance(ix, range):
-                parts.append(torch.arange(ix.start, ix.stop, ix.step, dtype=torch.int32, device=self.device))
-            else:
-                parts.append(torch.from_numpy(np.asarray(ix, dtype=np.int32)).to(self.device))
+        for q, ix in enumerate(idx_list):
+            if q in host_parts:
+                parts.append(torch.from_numpy(host_parts[q]).to(self.device))
+            else:      # device tensors (the device sampler's output) are trusted: checking would cost a sync
+                parts.append(ix.to(device=self.device, dtype=torch.int32).reshape(-1))
         return counts, torch.cat(parts).contiguous()
 
     def fwdbwd(self, batch, globals_f32, zmask_i64, counts_global=None):

@@ -140,10 +140,8 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         stepper = FusedStep(model, lr=lr, seed=seed)
     else:
         optimizer = torch.optim.Adam(model.parameters(), lr=lr)
-    best_mp = copy.deepcopy(model.mp)
-    best_vae = copy.deepcopy(model.y_vae)
     elbo_hist, trace = [], []
-    state = {'best_mp': best_mp, 'best_vae': best_vae}
+    state = {'best_mp': copy.deepcopy(model.mp)}
 
     def finish(t, elbo_t, ll, lp, lq, fixed_grad):
         """bookkeeping of step t (reference fit.py:109-141); True = stop"""
@@ -155,7 +153,6 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
                 elbo_hist[-1] / model.Nsum, ll / model.Nsum, lp / model.Nsum, lq / model.Nsum))
         if backup_every > 0 and t % backup_every == 0 and elbo_good:
             state['best_mp'] = copy.deepcopy(model.mp)
-            state['best_vae'] = model.y_vae
         if trace_every > 0 and t % trace_every == 0 and elbo_good:
             trace.append({key: copy.deepcopy(model.mp[key]) for key in model.mp})
         if t > 10 and abs(elbo_hist[-1] / elbo_hist[-2] - 1) < eps_conv:
@@ -208,7 +205,11 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         if finish(t, elbo_t, ll, lp, lq, fixed_grad):
             break
         t += 1
-    best_mp, best_vae = state['best_mp'], state['best_vae']
+    # like the reference, the result lives on the CPU and pickles without a GPU: 'mp' = the last good backup,
+    # 'vae' = the imputation parameters at return (reference fit.py:145-147 returns its live model.y_vae)
+    best_mp = {key: blk.to('cpu') for key, blk in state['best_mp'].items()}
+    best_vae = [v.to_cpu_copy() for v in model.y_vae]
+    trace = [{key: blk.to('cpu') for key, blk in snap.items()} for snap in trace]
     return {'elbo': elbo_hist, 'trace': trace, 'mp': best_mp, 'tau': tau, 'vae': best_vae,
             'use_stick_break': use_stick_break, 'y': y, 'priors': str(model.priors),
             'model_noisy': model_noisy}

@@ -61,6 +61,23 @@ class ModelParam:
         new.size, new.support = self.size, self.support
         return new
 
+    def to(self, device):
+        """Detached copy of this block on `device` (fit returns CPU copies like the reference)."""
+        new = ModelParam.__new__(ModelParam)
+        new.vp = torch.nn.Parameter(self.vp.detach().to(device, copy=True))
+        new.size, new.support = self.size, self.support
+        return new
+
+    # pickles hold only this block, on the CPU (vp may be a CUDA view into the fused step's flat buffer:
+    # the default pickle would carry that whole storage and need a GPU to load); the reference's callers
+    # pickle.dump fit's result (tests/test_model.py:41-43, sims/cb/cb.py:164)
+    def __getstate__(self):
+        return {'vp': self.vp.detach().cpu().clone(), 'size': self.size, 'support': self.support}
+
+    def __setstate__(self, state):
+        self.vp = torch.nn.Parameter(state['vp'])
+        self.size, self.support = state['size'], state['support']
+
     # -- q(real) = Normal(loc, scale); reference model_param.py:46-52
     def loc_scale(self):
         if self.support in ('simplex', 'unit_interval'):
@@ -98,6 +115,14 @@ class ModelParam:
         return (-0.5 * zed * zed - torch.log(scale) - HALF_LOG_2PI).sum()
 
 
+def _rebuild_vae(mean, log_sd):
+    v = VAE(mean.shape[1])
+    with torch.no_grad():
+        v.mean.copy_(mean)
+        v.log_sd.copy_(log_sd)
+    return v
+
+
 class VAE(torch.nn.Module):
     """Imputation parameters of one sample: Normal(mean_j, exp(log_sd_j)) per
     marker (reference vae.py:7-15; despite the name it is not a network).
@@ -111,6 +136,16 @@ class VAE(torch.nn.Module):
         super().__init__()
         self.mean = torch.nn.Parameter(torch.full((1, J), float(mean_init), dtype=F64, device=device))
         self.log_sd = torch.nn.Parameter(torch.full((1, J), math.log(sd_init), dtype=F64, device=device))
+
+    def to_cpu_copy(self):
+        new = VAE(self.mean.shape[1])
+        with torch.no_grad():
+            new.mean.copy_(self.mean.detach().cpu())
+            new.log_sd.copy_(self.log_sd.detach().cpu())
+        return new
+
+    def __reduce__(self):       # pickle as a CPU copy of the two rows (see ModelParam.__getstate__)
+        return (_rebuild_vae, (self.mean.detach().cpu().clone(), self.log_sd.detach().cpu().clone()))
 
     def forward(self, y_mini, m_mini, N_full, scale=1):
         from torch.distributions import normal as _tdn

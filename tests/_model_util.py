@@ -42,13 +42,22 @@ def apply_prior_spec(pri, spec):
     return pri
 
 
+def model_with_engine(factory):
+    """Test-only Model subclass whose per-cell engine is `factory` (e.g. tests/_stub_engine.OracleEngine,
+    the fp64 oracle on the CPU) -- the product class itself has no such seam."""
+    class StubbedModel(cy.model.Model):
+        def _make_engine(self, *args, **kwargs):
+            return factory(*args, **kwargs)
+    return StubbedModel
+
+
 def build_model(case, device, engine_factory=None, noise='external'):
     y = [t.clone() for t in case.y]
     pri = cy.model.default_priors(y, K=case.K, L=[case.L0, case.L1], y_bounds=[-5., -3.5, -2.])
     apply_prior_spec(pri, getattr(case, 'prior_spec', {}))
-    mod = cy.model.Model(y=y, priors=pri, tau=case.tau, verbose=-1, use_stick_break=case.stick,
-                         model_noisy=case.noisy, scale=case.scale, device=device, noise=noise,
-                         _engine_factory=engine_factory)
+    cls = cy.model.Model if engine_factory is None else model_with_engine(engine_factory)
+    mod = cls(y=y, priors=pri, tau=case.tau, verbose=-1, use_stick_break=case.stick,
+              model_noisy=case.noisy, scale=case.scale, device=device, noise=noise)
     assert list(mod.mp.keys()) == case.keys
     with torch.no_grad():
         for k in case.keys:

@@ -145,3 +145,74 @@ def test_pipelined_fit_schedule_never_runs_past_a_snapshot(max_iter, backup_ever
     if chunk > 1 and max_iter >= 4 * chunk and all(v % chunk == 0 for v in periods):
         # aligned snapshot periods (the defaults: 10 and max_iter / 50): all but the edges run inside chunks
         assert sum(n for _, n in sched if n > 1) >= max_iter + 1 - 2 * chunk
+
+
+def _write_cb_file(path, N, J, seed=0, na_rate=0.2, low_rate=0.01):
+    """A file in the cord-blood text format (reference cytofpy/util/readCB.py:3-28): header
+    `N n_1 ... n_I`, marker names, one row per cell, `NA` for missing."""
+    rng = np.random.default_rng(seed)
+    with open(path, 'w') as f:
+        f.write('N ' + ' '.join(str(n) for n in N) + '\n')
+        f.write(' '.join('M%d' % j for j in range(J)) + '\n')
+        for n in N:
+            y = rng.normal(0.0, 2.0, size=(n, J))
+            y[rng.random((n, J)) < low_rate] = -7.5           # cells preprocess() must drop
+            miss = (y < 0) & (rng.random((n, J)) < na_rate)
+            for row, mrow in zip(y, miss):
+                f.write(' '.join('NA' if mm else repr(float(v)) for v, mm in zip(row, mrow)) + '\n')
+
+
+def test_readcb_and_preprocess_match_the_reference_reader(tmp_path):
+    """f4: the same file through cytofpy_b200.util.readCB / preprocess and through the reference's reader
+    (imported from /root/reference when it is there: build container only) gives identical tensors."""
+    import os
+    import sys
+    N, J = [700, 450, 520], 32
+    p = tmp_path / 'cb.txt'
+    _write_cb_file(str(p), N, J)
+    d = cy.util.readCB(str(p))
+    assert d['N'] == N and len(d['markers']) == J and [tuple(t.shape) for t in d['y']] == [(n, J) for n in N]
+    assert all(t.dtype == torch.float64 for t in d['y'])
+    raw_nan = [int(torch.isnan(t).sum()) for t in d['y']]
+    assert all(c > 0 for c in raw_nan)
+    cy.util.preprocess(d, rm_cells_below=-6.0)
+    assert all(a < b for a, b in zip(d['N'], N))              # some cells went away
+    for yi, mi in zip(d['y'], d['m']):
+        assert bool(((yi > -6.0) | torch.isnan(yi)).all()) and torch.equal(mi, torch.isnan(yi))
+    if os.path.isdir('/root/reference/cytofpy'):
+        import subprocess
+        code = r"""
+import sys, torch, pickle
+sys.path.insert(0, '/root/reference')
+from cytofpy.util.readCB import readCB, preprocess
+d = readCB(%r); preprocess(d, rm_cells_below=-6.0)
+pickle.dump({'N': d['N'], 'y': [t.double() for t in d['y']], 'm': d['m'], 'markers': d['markers']}, open(%r, 'wb'))
+""" % (str(p), str(tmp_path / 'ref.p'))
+        out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        import pickle
+        ref = pickle.load(open(str(tmp_path / 'ref.p'), 'rb'))
+        assert ref['N'] == d['N'] and ref['markers'] == d['markers']
+        for a, b, ma, mb in zip(d['y'], ref['y'], d['m'], ref['m']):
+            # the reference parses into torch's default dtype at import order; values agree to fp32 at least
+            assert torch.allclose(torch.nan_to_num(a, nan=99.0), torch.nan_to_num(b, nan=99.0), rtol=1e-6, atol=0)
+            assert torch.equal(ma, mb)
+
+
+def test_model_param_and_vae_pickle_as_cpu_copies():
+    """f3: the blocks fit() returns pickle by value, on the CPU, whatever they were views of."""
+    import pickle
+    from cytofpy_b200.model.variational import ModelParam, VAE
+    flat = torch.arange(40, dtype=torch.float64)
+    blk = ModelParam((2, 5), 'simplex')
+    blk.vp = torch.nn.Parameter(flat[10:30].view(2, 2, 5))          # a view into a larger buffer
+    data = pickle.dumps({'W': blk, 'vae': [VAE(4, mean_init=-2.5, sd_init=.3)]})
+    assert len(data) < 4000                                          # not the whole 40-element storage + module state
+    back = pickle.loads(data)
+    assert torch.equal(back['W'].vp.detach(), blk.vp.detach()) and back['W'].support == 'simplex'
+    assert back['W'].dist().mean.shape == (2, 5)
+    v = back['vae'][0]
+    assert torch.allclose(v.mean, torch.full((1, 4), -2.5, dtype=torch.float64))
+    y = torch.tensor([[0.5, float('nan'), 1.0, -1.0]], dtype=torch.float64)
+    yi, lq = v(y, torch.isnan(y), 10)
+    assert yi.shape == (1, 4) and not torch.isnan(yi).any() and yi[0, 0] == 0.5

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from tests._golden import Case, rel
-from tests._model_util import build_model, model_grads, noise_queue, replay_noise
+from tests._model_util import build_model, model_grads, model_with_engine, noise_queue, replay_noise
 from tests._stub_engine import OracleEngine
 
 import cytofpy_b200 as cy
@@ -42,10 +42,9 @@ def _worker(rank, world, port, out_dir):
     lo, hi = _shard(c, rank, world)
     y = [t[a:b].clone() for t, a, b in zip(c.y, lo, hi)]
     pri = cy.model.default_priors(c.y, K=c.K, L=[c.L0, c.L1], y_bounds=[-5., -3.5, -2.])
-    mod = cy.model.Model(y=y, priors=pri, tau=c.tau, verbose=-1, use_stick_break=c.stick,
-                         model_noisy=c.noisy, scale=c.scale, device='cpu', noise='external',
-                         N_global=c.N, row_global=lo, dist_group=dist.group.WORLD,
-                         _engine_factory=OracleEngine)
+    mod = model_with_engine(OracleEngine)(y=y, priors=pri, tau=c.tau, verbose=-1, use_stick_break=c.stick,
+                                          model_noisy=c.noisy, scale=c.scale, device='cpu', noise='external',
+                                          N_global=c.N, row_global=lo, dist_group=dist.group.WORLD)
     with torch.no_grad():
         for k in c.keys:
             mod.mp[k].vp.copy_(torch.tensor(c.z['vp_' + k], dtype=F64))
