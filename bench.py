@@ -9,9 +9,12 @@ sample, transforms, per-cell ELBO forward+backward over ONE batch (the fused
 CUDA kernel), log prior, entropy, backward to every variational parameter, NaN
 scrub and the Adam step — here 5 kernel launches (cytofpy_b200/model/fused.py).  The default workload is BASELINE.json configs[3]
 ("cfg4": full batch, I=8, J=32, K=30, L=5/5) — the configuration the metric
-string names — with 1,000,000 cells PER GPU (weak scaling: rank r holds rows
-[r*125000, (r+1)*125000) of each of the 8 samples; one all-reduce of the
-~4.3k-float gradient block per step).  Prints ONE JSON line (rank 0).
+string names.  `--scaling strong` (default) is the split BASELINE.json states: the
+1,000,000 cells of the job are sharded over the N GPUs (rank r holds rows
+[r*125000/N, (r+1)*125000/N) of each of the 8 samples; the ~4.3k-double packed
+gradient block is summed over the ranks inside the finalise kernel).  With N > 1
+the same line carries the weak-scaling figure (1,000,000 cells PER GPU) under
+"weak"; `--scaling weak` makes that the headline instead.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -60,6 +63,22 @@ def measured_peak():
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def profiled_traffic(workload):
+    """dram__bytes_read + dram__bytes_write of ONE launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json: written next to the digest it was read from, with the sha1 of the kernel source it was
+    taken on).  None when there is no capture for this workload or the kernel source has changed since."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            rec = json.load(f)[workload]
+        with open(os.path.join(ROOT, rec['source']), 'rb') as f:
+            if hashlib.sha1(f.read()).hexdigest() != rec['source_sha1']:
+                return None
+        return float(rec['dram_bytes_per_launch'])
+    except Exception:
+        return None
 
 
 def make_data(w, seed):
@@ -135,39 +154,84 @@ def time_cpu_port(w, steps, warmup, cells_per_sample, threads=None):
     return cells / med, torch.get_num_threads(), cells, med
 
 
+REFERENCE_DIR = '/root/reference'
+
+
+def time_cpu_reference(w, steps, warmup, cells_per_sample, threads=None):
+    """The UNMODIFIED reference (`cytofpy.model.update`, imported from /root/reference -- present in the build
+    container only) on the same bounded sample as time_cpu_port.  Only shim: validate_args off (reference vae.py:29
+    builds Normal(., 0), which torch >= 1.8 rejects by default)."""
+    sys.path.insert(0, REFERENCE_DIR)
+    torch.distributions.Distribution.set_default_validate_args(False)
+    import cytofpy
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    ws = dict(w, n=cells_per_sample)
+    y = [torch.tensor(a, dtype=torch.float64) for a in make_data(ws, seed=0)]
+    kw = w['kw']
+    pri = cytofpy.model.default_priors(y, K=w['K'], L=[w['L0'], w['L1']], y_bounds=[-5., -3.5, -2.])
+    mod = cytofpy.model.Model(y=y, priors=pri, tau=kw.get('tau', .1), verbose=-1,
+                              use_stick_break=kw.get('use_stick_break', True), scale=kw.get('scale', 1.0))
+    opt = torch.optim.Adam(mod.parameters(), lr=1e-2)
+    mb = w['mb'] if w['mb'] and w['mb'] < cells_per_sample else None
+    times, cells = [], 0
+    for t in range(warmup + steps):
+        t0 = time.perf_counter()
+        idx = [np.arange(cells_per_sample) if mb is None else np.random.choice(cells_per_sample, mb, replace=False)
+               for _ in range(w['I'])]
+        cytofpy.model.update(opt, mod, idx)
+        if t >= warmup:
+            times.append(time.perf_counter() - t0)
+            cells = sum(len(ix) for ix in idx)
+    med = statistics.median(times)
+    return cells / med, torch.get_num_threads(), cells, med
+
+
+def time_cpu(w, steps, warmup, cells_per_sample, threads=None):
+    """(cells/s, threads, cells per step, seconds per step, kind): the reference itself where it is on the machine,
+    else its oracle port"""
+    if os.path.isdir(os.path.join(REFERENCE_DIR, 'cytofpy')):
+        try:
+            return time_cpu_reference(w, steps, warmup, cells_per_sample, threads) + ('reference',)
+        except Exception as e:      # e.g. an incompatible torch: fall back to the port, say so on stderr
+            sys.stderr.write('bench: reference import failed (%s), timing the oracle port\n' % e)
+    return time_cpu_port(w, steps, warmup, cells_per_sample, threads) + ('port',)
+
+
 def run_reference(args, w, rank, world):
     if rank != 0:
         return
     per = min(w['n'], 4000 if w['mb'] is None else w['n'])
     # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
     threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    v, cores, cells, med = time_cpu_port(w, args.steps, args.warmup, per, threads=threads)
-    sample = 'oracle port of reference update (fp64 torch CPU, autograd, Adam) on %d cells/step ' \
-             '(%d samples x %d%s) at the workload J/K/L' % (cells, w['I'], per,
-                                                           '' if w['mb'] is None else ', minibatch %d' % w['mb'])
+    v, cores, cells, med, kind = time_cpu(w, args.steps, args.warmup, per, threads=threads)
+    sample = '%s update (fp64 torch CPU, autograd, Adam) on %d cells/step ' \
+             '(%d samples x %d%s) at the workload J/K/L' % (
+                 'the reference (cytofpy.model.update from /root/reference)' if kind == 'reference'
+                 else 'oracle port of the reference', cells, w['I'], per,
+                 '' if w['mb'] is None else ', minibatch %d' % w['mb'])
     emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': args.workload, 'I': w['I'], 'J': w['J'], 'K': w['K'], 'L': [w['L0'], w['L1']]},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     })
 
 
-def run_ours(args, w, rank, world, local_rank):
+def build_job(args, w, rank, world, dev, group, scaling):
+    """This rank's shard of the workload and the fused step that trains on it.  strong: the workload's cells (and its
+    minibatch) are divided over the ranks; weak: every rank holds the whole workload size."""
     import cytofpy_b200 as cy
-    from cytofpy_b200.model.engine import Batch
-    dev = torch.device('cuda', local_rank)
-    torch.cuda.set_device(dev)
-    group = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
-        group = dist.group.WORLD
-    I, n, J = w['I'], w['n'], w['J']
-    y_np = make_data(w, seed=1000 + rank)                      # this rank's rows
-    y = [torch.from_numpy(a) for a in y_np]
+    from cytofpy_b200.model.fused import FusedStep
+    I = w['I']
+    n = w['n'] // world if scaling == 'strong' else w['n']
+    mb = None if w['mb'] is None else (max(1, w['mb'] // world) if scaling == 'strong' else w['mb'])
+    y_np = [a[:n] for a in make_data(w, seed=1000 + rank)]   # this rank's rows
+    y = [torch.from_numpy(np.ascontiguousarray(a)) for a in y_np]
     N_global = [n * world] * I
     pri_y = [t[:2000].double() for t in y]
     priors = cy.model.default_priors(pri_y, K=w['K'], L=[w['L0'], w['L1']], y_bounds=[-5., -3.5, -2.])
@@ -175,10 +239,10 @@ def run_ours(args, w, rank, world, local_rank):
     torch.manual_seed(1)
     model = cy.model.Model(y=y, priors=priors, verbose=-1, device=dev, noise='philox', seed=1,
                            N_global=N_global, row_global=[rank * n] * I, dist_group=group, **w['kw'])
-    from cytofpy_b200.model.fused import FusedStep
     fs = FusedStep(model, lr=1e-2, seed=1, allreduce=args.allreduce)   # the path cytofpy_b200.model.fit drives
-    mb = w['mb']
-    n_sampler = 0 if mb is None else I
+
+    def draw_idx(t):
+        return [range(n)] * I if mb is None else cy.model.device_minibatch(model, mb, t, 1)
 
     def one_step(t):
         # after the first (host-driven) warm-up step the whole step is ONE CUDA-graph replay
@@ -188,19 +252,14 @@ def run_ours(args, w, rank, world, local_rank):
             fs.capture(mb)
         return fs.graph_step()
 
-    def draw_idx(t):
-        return [range(n)] * I if mb is None else cy.model.device_minibatch(model, mb, t, 1)
+    return dict(model=model, fs=fs, y=y, n=n, mb=mb, one_step=one_step, draw_idx=draw_idx,
+                cells_step=I * (n if mb is None else mb), scaling=scaling)
 
-    cells_step = I * (n if mb is None else mb)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    eng = model.engine
 
-    # ---- device-resident throughput: K timed steps, L2 flushed between them
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize(dev)
-
+def timed_steps(job, args, dev, flush, barrier, local_rank):
+    """W warm-up steps, then K steps timed one by one with CUDA events on the launching stream (L2 flushed before
+    each); returns (mean ms per step, launches inside the timed region, clock summary)."""
+    fs, one_step = job['fs'], job['one_step']
     for t in range(args.warmup):
         one_step(t)
     barrier()
@@ -218,7 +277,35 @@ def run_ours(args, w, rank, world, local_rank):
     barrier()
     sampler.stop_flag = True
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    launches = fs.launches - launches0      # graph_step counts the sampler kernels itself
+    return step_ms, fs.launches - launches0, sampler.summary()      # graph_step counts the sampler kernels itself
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import cytofpy_b200 as cy
+    from cytofpy_b200.model.engine import Batch
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+        group = dist.group.WORLD
+    scaling = args.scaling
+    job = build_job(args, w, rank, world, dev, group, scaling)
+    model, fs, y, n, mb = job['model'], job['fs'], job['y'], job['n'], job['mb']
+    I, J = w['I'], w['J']
+    one_step, draw_idx = job['one_step'], job['draw_idx']
+    cells_step = I * (n if mb is None else mb)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    eng = model.engine
+
+    # ---- device-resident throughput: K timed steps, L2 flushed between them
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    step_ms, launches, clocks = timed_steps(job, args, dev, flush, barrier, local_rank)
 
     fs.release_graph()
     # ---- dominant kernel alone (CUDA events on the launching stream, L2 flushed)
@@ -309,42 +396,64 @@ def run_ours(args, w, rank, world, local_rank):
     barrier()
     e2e_ms = e_ev[0][0].elapsed_time(e_ev[0][1]) / e2e_div
 
-    times = torch.tensor([step_ms, k_ms, e2e_ms], dtype=torch.float64, device=dev)
+    peers_desc = 'single GPU: none' if world == 1 else (
+        'fused into the finalise kernel, NVLink peer stores' if fs.peers is not None else 'NCCL')
+    # ---- N > 1: the OTHER scaling mode, device-resident steps only, in the same run
+    other, other_ms, other_cells = None, 0.0, 0
+    if world > 1 and not args.one_mode:
+        other = 'weak' if scaling == 'strong' else 'strong'
+        fs.release_graph()
+        if fs.peers is not None:
+            fs.peers.close()
+        del model, fs, job, y_pin
+        torch.cuda.empty_cache()
+        job2 = build_job(args, w, rank, world, dev, group, other)
+        other_ms, _, _ = timed_steps(job2, args, dev, flush, barrier, local_rank)
+        other_cells = job2['cells_step']
+        peers2 = job2['fs'].peers is not None
+        job2['fs'].release_graph()
+
+    times = torch.tensor([step_ms, k_ms, e2e_ms, other_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
-    step_ms, k_ms_max, e2e_ms = times.tolist()
+    step_ms, k_ms_max, e2e_ms, other_ms = times.tolist()
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             per = min(n, 4000 if mb is None else n)
-            v, cores, cells, med = time_cpu_port(w, 3, 1, per)
-            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': 'oracle port of reference update (fp64 torch CPU) on %d cells/step at the '
-                             'workload J/K/L, median of 3 steps' % cells}
+            v, cores, cells, med, kind = time_cpu(w, 3, 1, per)
+            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                   'sample': '%s update (fp64 torch CPU) on %d cells/step at the workload J/K/L, median of 3 steps' % (
+                       'reference' if kind == 'reference' else 'oracle port of the reference', cells)}
         out = {
             'metric': METRIC, 'value': cells_step * world / (step_ms * 1e-3), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': args.workload, 'I': I, 'cells_per_gpu': I * n, 'cells_per_step_per_gpu': cells_step,
+            'config': {'workload': args.workload, 'I': I, 'cells_total': I * n * world, 'cells_per_gpu': I * n,
+                       'cells_per_step_per_gpu': cells_step,
                        'J': J, 'K': w['K'], 'L': [w['L0'], w['L1']], 'minibatch': mb, 'nan_rate': w['nan'],
-                       'parallelism': 'cells sharded x%d, all-reduce of gradient block (%s)' % (
-                           world, 'single GPU: none' if world == 1 else (
-                               'fused into the finalise kernel, NVLink peer stores' if fs.peers is not None else 'NCCL')),
+                       'parallelism': 'cells sharded x%d, all-reduce of gradient block (%s)' % (world, peers_desc),
                        'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox',
                        'step': 'one CUDA-graph replay (device sampler, global fwd, per-cell kernel, finalise, global bwd + Adam)'},
             'e2e': {'value': cells_step * world / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms},
             'gpu_launches': int(launches),
-            'clocks': sampler.summary(),
+            'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_mma_kernel (+finalize)', 'achieved': achieved,
                          'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         # dram__bytes_read+write of one launch, ncu --set full (profiles/README.md)
-                         'traffic': 131.5e6 if args.workload == 'cfg4' else None,
+                         # dram__bytes_read+write of one launch of that kernel on this workload's full size, from the
+                         # committed ncu capture (profiles/traffic.json); None if the kernel changed since
+                         'traffic': profiled_traffic(args.workload) if (world == 1 or scaling == 'weak') else None,
                          'peak_source': peak_src, 'bytes_per_cell': bytes_cell, 'kernel_ms': k_ms,
                          'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
             'cpu_baseline': cpu,
         }
+        if other is not None:
+            out[other] = {'scaling': other, 'value': other_cells * world / (other_ms * 1e-3), 'unit': UNIT,
+                          'ms_per_step': other_ms, 'cells_total': other_cells * world,
+                          'cells_per_step_per_gpu': other_cells,
+                          'note': 'same run, device-resident steps, L2 flushed, CUDA events, max over ranks'}
         emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -364,6 +473,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
+                    help='N>1: strong = the workload is divided over the GPUs (BASELINE.json: "1M cells ... sharded across '
+                         '8 B200"), weak = every GPU holds the whole workload size; the other mode is reported under its own key')
+    ap.add_argument('--one-mode', action='store_true', help='N>1: skip the measurement of the other scaling mode')
     ap.add_argument('--allreduce', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='N>1: one-shot all-reduce over peer memory fused into the finalise kernel (auto: NCCL if the '
                          'mailboxes cannot be mapped), or NCCL')

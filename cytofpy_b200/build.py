@@ -10,9 +10,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, '_C')
 LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200.so')
-# same sources with the dZ accumulation on tcgen05.mma + TMEM (csrc/elbo_kernel_mma.cuh, CYTOF_TMEM_DZ):
-# measured 5 % slower than the default at cfg4, kept as a tested variant (tests/test_gpu_tmem_variant.py)
-TMEM_LIB_PATH = os.path.join(OUT_DIR, 'libcytof_b200_tmem.so')
 SOURCES = ['variants_mma64.cu', 'variants_mma.cu', 'variants_umma.cu', 'elbo_kernel.cu', 'global_part.cu', 'labels.cu', 'abi.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC']
@@ -64,12 +61,6 @@ def build(force=False, verbose=False, defines=(), out=None):
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
     return target
-
-
-def build_tmem_variant(force=False):
-    if not force and not _stale(TMEM_LIB_PATH):
-        return TMEM_LIB_PATH
-    return build(defines=['CYTOF_TMEM_DZ=1'], out=TMEM_LIB_PATH)
 
 
 if __name__ == '__main__':

@@ -454,7 +454,9 @@ constexpr int kFinLanes = CYTOF_FIN_LANES;     // 8, 16 or 32 lanes per output
 // rank owns a mailbox (cudaMalloc'ed by cytof_peer_alloc, mapped into the peers with CUDA IPC):
 //   [0, 128)    uint64 flags[src]: sequence number of the last step rank `src` has delivered
 //   [128, 132)  uint32 ticket: CTAs of the local finalise kernel that are done (local use)
-//   [132, 136)  uint32 error: set when a wait timed out
+//   [132, 136)  uint32 error: set when a wait of THIS rank timed out (sticky until the mailbox is freed)
+//   [136, 140)  uint32 abort: set by ANY rank whose wait timed out (it stores it into every mailbox), so that all
+//               ranks poison their results and raise together instead of diverging silently
 //   [256, ...)  double slots[parity][src][nout]: the packed vector of rank `src` for steps of that parity
 // Step s: every finalise thread stores its output straight into slot [s & 1][rank] of EVERY mailbox
 // (its own included); the last CTA of the grid publishes flags[rank] = s to every peer with a
@@ -469,6 +471,7 @@ struct PeerArgs {
   unsigned char* mailbox[CYTOF_MAX_PEERS];
 };
 constexpr size_t kPeerHeaderBytes = 256;
+
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
@@ -588,6 +591,7 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   unsigned char* mine = peer.mailbox[peer.rank];
   unsigned* ticket = reinterpret_cast<unsigned*>(mine + 128);
   unsigned* errw = reinterpret_cast<unsigned*>(mine + 132);
+  volatile unsigned* abortw = reinterpret_cast<volatile unsigned*>(mine + 136);
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
   __syncthreads();
   if (!s_last) return;
@@ -598,11 +602,17 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + threadIdx.x;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < seq) {
-      if (clock64() - t0 > 4000000000ll) { *errw = 1u; break; }    // ~2 s: a peer died; never hang the GPU
+      if (*abortw != 0u) break;                                    // another rank gave up: do not wait out the 2 s
+      if (clock64() - t0 > 4000000000ll) {                         // ~2 s: a peer died; never hang the GPU
+        *errw = 1u;
+        for (int q = 0; q < peer.world; ++q) *reinterpret_cast<volatile unsigned*>(peer.mailbox[q] + 136) = 1u;
+        __threadfence_system();
+        break;
+      }
     }
   }
   __syncthreads();
-  const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u;
+  const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u || *abortw != 0u;
   const double* slots = reinterpret_cast<const double*>(mine + kPeerHeaderBytes) + (size_t)par * peer.world * peer.nout;
   // one CTA sums world x nout doubles: all loads of two outputs (up to 32) are issued before the first add,
   // otherwise this tail is a chain of L2 round trips; the sum runs in rank order on every rank (x + 0.0 = x)
@@ -617,7 +627,10 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     double a = 0.0, c = 0.0;
 #pragma unroll
     for (int q = 0; q < CYTOF_MAX_PEERS; ++q) { a += v[q]; c += w[q]; }
-    if (bad) a = c = __longlong_as_double(0x7ff8000000000000ll);
+    if (bad) {      // NaN everywhere, +inf in the ll slot: the mark global_adam_body reads as "the exchange failed"
+      a = (o == peer.nout - 2) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0x7ff8000000000000ll);
+      c = (o2 == peer.nout - 2) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0x7ff8000000000000ll);
+    }
     packed[o] = a;
     if (o2 < peer.nout) packed[o2] = c;
   }

@@ -26,17 +26,12 @@
 
 namespace cytof {
 
-#ifndef CYTOF_TMEM_DZ
-#define CYTOF_TMEM_DZ 0   // 1: dZ += D^T g as ONE tcgen05.mma (TF32, M = N = 64, K = 8) per tile, accumulators in TMEM
-#endif
-constexpr int kMmaUFloats = CYTOF_TMEM_DZ ? 2 * 2 * 512 : 0;    // per warp: A and B operand tiles, double-buffered (2 KB each)
-constexpr int kMmaHdrFloats = CYTOF_TMEM_DZ ? 64 : 0;           // CTA header: 2 mbarriers per warp + TMEM base
 constexpr int kTile = 8;                 // cells per warp iteration (= N of the MMAs)
 constexpr int kTS = 36;                  // row stride of the per-warp tiles: conflict-free ldmatrix
 constexpr int kTileFloats = kTile * kTS;
 // per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
-constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 32 + 2 * kTile * 32 + 12 * 32 + kMmaUFloats;   // sW: 12 rows (Philox staging)
-constexpr int kMmaZFloats = 2 * 8 * 32 * 4 + kMmaHdrFloats;     // A-fragment tables of Z^T and Z (+ header)
+constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 32 + 2 * kTile * 32 + 12 * 32;   // sW: 12 rows (Philox staging)
+constexpr int kMmaZFloats = 2 * 8 * 32 * 4;     // A-fragment tables of Z^T and Z
 
 
 // Packed fp32 through the CUDA 12.9 sm_100 intrinsics (FFMA2 / FADD2 / FMUL2 on float2): unlike
@@ -172,12 +167,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   float* sS = sR1 + kTile * 32;            // [0..7] fac*rho, [8..15] fac*(1-rho), [16..23] fac*rho/sum_k e_k per cell
   float* sYb = sS + 32;                    // [2][8][32] y rows, double buffered
   float* sW = sYb + 2 * kTile * 32;        // [8][32] sum_l w d (imputation gradient); [12][32] normals during the pre-pass
-#if CYTOF_TMEM_DZ
-  unsigned char* sUA = reinterpret_cast<unsigned char*>(sW + 12 * 32);   // [2][2 KB] A = [D_hi ; D_lo] (64 x 8), K-major
-  unsigned char* sUB = sUA + 2 * 2048;                                      // [2][2 KB] B = [g_hi ; g_lo] (64 x 8)
-  unsigned long long* mbars = reinterpret_cast<unsigned long long*>(smem + 2 * 8 * 32 * 4) + 2 * warp;   // [2] per warp
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + 2 * 8 * 32 * 4 + 32);
-#endif
   float* sred = smem;                      // final reduction aliases everything (after the loop)
 
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
@@ -216,18 +205,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     }
   }
 
-#if CYTOF_TMEM_DZ
-  // all 512 TMEM columns: one 64 x 64 fp32 accumulator (64 columns) per warp (the kernel runs one CTA per SM)
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_base_s)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbars)) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbars + 1)) : "memory");
-  }
-  for (int e = lane; e < 2 * 2 * 512; e += 32) reinterpret_cast<float*>(sUA)[e] = 0.f;     // rows >= J / K stay zero
-#endif
 
   // ---------------- per-sample constants -> registers ----------------
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
@@ -296,22 +273,18 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   // sum_n (c0 y0'^2 + c1 y1'^2)
   float2 sw[NPT], swy[NPT];
   float sq = 0.f;
-#if !CYTOF_TMEM_DZ
   float dZ[2][4][4];                     // C fragments of dZ (permuted rows / columns, see epilogue)
-#endif
   float gW[4] = {0.f, 0.f, 0.f, 0.f};    // sum_n g_k for k = g, g+8, g+16, g+24 (this thread's 2 cells)
   float dvm = 0.f, dvls = 0.f, nm = 0.f, sfr = 0.f, sfo = 0.f, lqy_l = 0.f, lmiss_l = 0.f;
   double ll2 = 0.0;
 #pragma unroll
   for (int q = 0; q < NPT; ++q) sw[q] = swy[q] = bcp(0.f);
-#if !CYTOF_TMEM_DZ
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int c = 0; c < 4; ++c) dZ[a][b][c] = 0.f;
-#endif
 
   // ---------------- stream the cells of this CTA, 8 per warp iteration ----------------
   const int32_t* __restrict__ idx = p.idx + (HAS_IDX ? (cb + c_lo) : 0);
@@ -448,26 +421,13 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     st.yy = yv * yv;
     return st;
   };
-#if CYTOF_TMEM_DZ
-  float udh[4], udl[4];        // hi / lo of D of four consecutive cells: one 16-byte store each into the A operand tile
-#endif
-  auto phase_a2 = [&](const int u, const AState& st, const int ub) {
+  auto phase_a2 = [&](const int u, const AState& st) {
     const float A0 = st.B0 + fast_lg2(st.S0), A1 = st.B1 + fast_lg2(st.S1);
     const float rr = fast_rcp(st.S0 * st.S1);      // one reciprocal for both mixtures (S in [1, L])
     reinterpret_cast<float2*>(sR0)[u * 32 + lane] = make_float2(rr * st.S1, rr * st.S0);   // 1/S0, 1/S1
     sD[u * kTS + lane] = A1 - A0;           // markers >= J: Z has zero rows there, the value is never used
     sA[u * kTS + lane] = okf * A0;
     if (NOISY) sY[u * kTS + lane] = st.yy;
-#if CYTOF_TMEM_DZ
-    {
-      split_trunc(okf * (A1 - A0), udh[u & 3], udl[u & 3]);
-      if ((u & 3) == 3) {      // rows lane (hi) and 32 + lane (lo), k = cells 4 (u / 4) .. + 3
-        unsigned char* base = sUA + ub * 2048 + (lane >> 3) * 256 + (u >> 2) * 128 + (lane & 7) * 16;
-        *reinterpret_cast<float4*>(base) = make_float4(udh[0], udh[1], udh[2], udh[3]);
-        *reinterpret_cast<float4*>(base + 1024) = make_float4(udl[0], udl[1], udl[2], udl[3]);
-      }
-    }
-#endif
   };
 
   // mixtures of cell u, backward: w_zl = c_z p_zl; statistics sum w and sum w y' per component,
@@ -513,23 +473,16 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 #pragma unroll
       for (int u = 1; u < kTile; ++u) {
         const AState now = phase_a1(u, sYb, missmask);
-        phase_a2(u - 1, prev, 0);
+        phase_a2(u - 1, prev);
         prev = now;
       }
-      phase_a2(kTile - 1, prev, 0);
+      phase_a2(kTile - 1, prev);
     }
     if (t0 + STRIDE < ncell) issue_tile(t0 + STRIDE, 1);
   }
   __syncthreads();   // Z tables visible
-#if CYTOF_TMEM_DZ
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_base_s;
-  const uint32_t tmem_acc = tmem_base + 64u * (uint32_t)warp;       // columns [64 warp, 64 warp + 64)
-#endif
 
-  int seq = 0;            // this warp's tile counter (operand / mbarrier double buffer index = seq & 1)
-  bool umma_ok = true;
-  for (; t0 < ncell; t0 += STRIDE, cur ^= 1, ++seq) {
+  for (; t0 < ncell; t0 += STRIDE, cur ^= 1) {
     const int nvalid = min(kTile, ncell - t0);
     const bool has_next = t0 + STRIDE < ncell;
     __syncwarp();
@@ -687,33 +640,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       sA[(ca + 1) * kTS + 16 * mt + g + 8] = sc2[1] * cT[mt][3];
     }
 
-#if CYTOF_TMEM_DZ
-    // ================= contraction 3: dZ += [D_hi ; D_lo]^T [g_hi | g_lo] as ONE tcgen05.mma =================
-    // (TF32, M = N = 64, K = 8 cells, accumulator of this warp in TMEM).  The A operand tile was
-    // written by the forward of this tile (phase_a2); the B operand tile is written here from the
-    // accumulator layout: rows = features (hi, then lo at +32), k = cells 2 t4, 2 t4 + 1.
-    {
-      unsigned char* ub = sUB + (seq & 1) * 2048 + (t4 >> 1) * 128 + g * 16 + (t4 & 1) * 8;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {       // feature 16 mt + g + 8 h: row group 2 mt + h
-          float ah, al3, bh2, bl2;
-          split_trunc(sc2[0] * ex[mt][2 * h], ah, al3);
-          split_trunc(sc2[1] * ex[mt][2 * h + 1], bh2, bl2);
-          *reinterpret_cast<float2*>(ub + (2 * mt + h) * 256) = make_float2(ah, bh2);
-          *reinterpret_cast<float2*>(ub + (2 * mt + h) * 256 + 1024) = make_float2(al3, bl2);
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core reads
-      __syncwarp();
-      if (lane == 0) {
-        umma_tf32(tmem_acc, umma_desc_kmajor(sUA + (seq & 1) * 2048), umma_desc_kmajor(sUB + (seq & 1) * 2048), seq > 0 ? 1u : 0u);
-        umma_commit(mbars + (seq & 1));
-      }
-    }
-    __syncwarp();
-#else
     // ================= contraction 3: dZ[j, k] += D^T . g over the 8 cells (tensor cores) =================
     // issued last: nothing in this tile's backward depends on it
     {
@@ -748,7 +674,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     }
     __syncwarp();
 
-#endif
 
 #ifdef CYTOF_PHASE_CLOCKS
     const long long ck1 = clock64();
@@ -759,10 +684,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     // registers cell u of this tile has just released -- one basic block, both pipes busy
     const float* ycur = sYb + cur * (kTile * 32);
     unsigned miss_n = 0u, any_n = 0u;
-#if CYTOF_TMEM_DZ
-    // the next tile's operands go to buffer (seq + 1) & 1: its previous MMA (tile seq - 1) must be done
-    if (has_next && seq >= 1) umma_ok = mbar_wait(mbars + ((seq + 1) & 1), (uint32_t)(((seq + 1) >> 1) - 1) & 1u) && umma_ok;
-#endif
     if (has_next) {
       const float* ynxt = sYb + (cur ^ 1) * (kTile * 32);
       cp_async_wait<0>();
@@ -775,10 +696,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       for (int u = 1; u < kTile; ++u) {
         phase_b(u, ycur, missmask, anymask);
         const AState now = phase_a1(u, ynxt, miss_n);
-        phase_a2(u - 1, prev, (seq + 1) & 1);
+        phase_a2(u - 1, prev);
         prev = now;
       }
-      phase_a2(kTile - 1, prev, (seq + 1) & 1);
+      phase_a2(kTile - 1, prev);
 #else
 #pragma unroll
       for (int u = 0; u < kTile; ++u) phase_b(u, ycur, missmask, anymask);
@@ -786,10 +707,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 #pragma unroll
       for (int u = 1; u < kTile; ++u) {
         const AState now = phase_a1(u, ynxt, miss_n);
-        phase_a2(u - 1, prev, (seq + 1) & 1);
+        phase_a2(u - 1, prev);
         prev = now;
       }
-      phase_a2(kTile - 1, prev, (seq + 1) & 1);
+      phase_a2(kTile - 1, prev);
 #endif
     } else {
 #pragma unroll
@@ -865,16 +786,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   ll2 += __shfl_xor_sync(FULL, ll2, 2);
 
   float* mine = sred + warp * pl.total;
-#if CYTOF_TMEM_DZ
-  // this warp's last MMA on each operand buffer has completed (=> all of them: they execute in order)
-  if (seq >= 1) umma_ok = mbar_wait(mbars + ((seq - 1) & 1), (uint32_t)((seq - 1) >> 1) & 1u) && umma_ok;
-  if (seq >= 2) umma_ok = mbar_wait(mbars + (seq & 1), (uint32_t)((seq - 2) >> 1) & 1u) && umma_ok;
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-#endif
   __syncthreads();            // every warp is done with its tiles and with the Z tables
-#if CYTOF_TMEM_DZ
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
   for (int t = lane; t < pl.total; t += 32) mine[t] = 0.f;
   __syncwarp();
   if (ok) {
@@ -888,44 +800,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     mine[pl.dvls + lane] = dvls;
     mine[pl.nm + lane] = nm;
   }
-#if CYTOF_TMEM_DZ
-  // accumulator a (of warp a): rows 16 q .. 16 q + 15 in TMEM lanes 32 q .. 32 q + 15; this warp can
-  // read quadrant q = warp % 4 and takes the accumulators a = warp / 4, warp / 4 + 2, ... in order.
-  // Rows 0..31 = D_hi markers (columns 0..31 hi features, 32..63 lo features), rows 32..63 = D_lo.
-  {
-    const int q = warp & 3;
-    const int ntile_cta = (ncell + kTile - 1) / kTile;
-    const int j = 16 * (q & 1) + lane;                   // marker of this lane's row (lanes 0..15)
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      if (q >= 2 && c0 >= 32) break;                     // D_lo g_lo is below the fp32 round-off: dropped
-      float acc[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-#pragma unroll 1
-      for (int a = (warp >> 2); a < kWarps; a += 2) {
-        if (a >= ntile_cta) continue;                    // that warp had no tile: its accumulator was never written
-        uint32_t r[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + 64u * (uint32_t)a + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] += __uint_as_float(r[c]);
-      }
-      if (lane < 16 && j < J) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int k = (c0 + c) & 31;
-          if (k < K) mine[pl.dZ + k * J + j] += umma_ok ? acc[c] : __int_as_float(0x7fc00000);
-        }
-      }
-    }
-  }
-#else
   // dZ fragments: (mt, nt, r) -> marker 4g + 2mt + (r >> 1), feature 8 t4 + 4 (r & 1) + nt
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -936,7 +810,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
         const int j = 4 * g + 2 * mt + (r >> 1), k = 8 * t4 + 4 * (r & 1) + nt;
         if (j < J && k < K) mine[pl.dZ + k * J + j] = dZ[mt][nt][r];
       }
-#endif
   if (t4 == 0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) if (g + 8 * r < K) mine[pl.gW + g + 8 * r] = gW[r];
@@ -968,11 +841,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     for (int w = 0; w < kWarps; ++w) a += reinterpret_cast<const double*>(sred + w * pl.total + pl.dbl)[threadIdx.x];
     reinterpret_cast<double*>(out + pl.dbl)[threadIdx.x] = a;
   }
-#if CYTOF_TMEM_DZ
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
-#endif
 }
 
 }  // namespace cytof

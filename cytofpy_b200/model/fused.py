@@ -1,8 +1,8 @@
 """The whole ADVI step as five kernel launches behind the C ABI (global fwd 1, per-cell 2, global bwd 1, Adam 1):
 
-    [cytof_sample_minibatch x I]  ->  cytof_global_fwd_f64  ->  cytof_elbo_fwdbwd_packed (2 kernels)
-        ->  [NCCL all-reduce of the packed gradient block when cells are sharded]
-        ->  cytof_global_bwd_adam_f64
+    [cytof_sample_minibatch_multi]  ->  cytof_global_fwd_f64  ->  cytof_elbo_fwdbwd_allreduce / _packed (2 kernels;
+        with cells sharded over GPUs the finalise kernel also sums the packed gradient block over the ranks
+        through peer memory, or NCCL does)  ->  cytof_global_bwd_adam_f64
 
 replacing one reference `update` (fit.py:32-48: Model.forward, backward, NaN scrub, Adam),
 which dispatches ~5,000 ATen ops and syncs the host 4 times.  All variational parameters live
@@ -100,8 +100,8 @@ class FusedStep:
         # launches of the global part (csrc/global_part.cu): the scans run in the last CTA of the element
         # kernels when their operands fit in shared memory (200 KB), else as kernels of their own
         smem = 200 * 1024
-        self._global_launches = ((1 if 16 * self.R <= smem else 2) +
-                                 (2 if 8 * (2 * self.R + self.packed.numel()) <= smem else 3))
+        self._fwd_launches = 1 if 16 * self.R <= smem else 2
+        self._global_launches = self._fwd_launches + (2 if 8 * (2 * self.R + self.packed.numel()) <= smem else 3)
         self.scalars_in, self.scalars = z(2), z(5)
         self.globals = z(self.eng.g_off[-1], torch.float32)
         o = self.eng.g_off
@@ -124,6 +124,22 @@ class FusedStep:
                     raise
                 self.peers = None      # 'auto': every rank raised together (peer.py) -> NCCL all-reduce on all ranks
         self._bind()
+
+    def _cells_and_tail(self, batch, cg, update, stream, step_dev=None):
+        """per-cell kernel -> packed (summed over ranks) -> backward of the global part -> Adam"""
+        m, eng, g = self.model, self.eng, self.g
+        if self.peers is not None:      # sum over ranks fused into the finalise kernel (NVLink P2P)
+            eng.fwdbwd_allreduce(batch, self.globals, self.zmask, self.packed, cg, self.peers)
+        else:
+            eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, cg)
+            if m.dist_group is not None:
+                torch.distributed.all_reduce(self.packed, group=m.dist_group)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.cytof_global_bwd_adam_f64(
+                C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
+                _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
+                _ptr(step_dev), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
+        return 2 + self._global_launches - self._fwd_launches
 
     def _bind(self):
         """copy the model's current parameters into theta and re-point them to views of it"""
@@ -163,19 +179,8 @@ class FusedStep:
             _lib.check(self.lib.cytof_global_fwd_f64(
                 C.byref(g), _ptr(self.theta), _ptr(global_noise), _ptr(self.stash), _ptr(self.globals),
                 _ptr(self.zmask), _ptr(self.scalars_in), stream))
-        if self.peers is not None:      # sum over ranks fused into the finalise kernel (NVLink P2P)
-            eng.fwdbwd_allreduce(batch, self.globals, self.zmask, self.packed, m._counts_global(batch),
-                                 self.peers)
-        else:
-            eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, m._counts_global(batch))
-            if m.dist_group is not None:
-                torch.distributed.all_reduce(self.packed, group=m.dist_group)
-        with torch.cuda.device(self.dev):
-            _lib.check(self.lib.cytof_global_bwd_adam_f64(
-                C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
-                _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
-                _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
-        self.launches += 2 + self._global_launches      # per-cell (2) + global fwd, bwd, Adam
+        self.launches += self._fwd_launches + self._cells_and_tail(batch, m._counts_global(batch), update, stream)
+        assert self.peers is None or self.peers.seq == self.t, 'peer sequence and step count must run in lock step'
         return self.scalars
 
     # ------------------------------------------------------------------ CUDA graph
@@ -220,24 +225,17 @@ class FusedStep:
                 _lib.check(self.lib.cytof_global_fwd_f64(
                     C.byref(g), _ptr(self.theta), _ptr(None), _ptr(self.stash), _ptr(self.globals),
                     _ptr(self.zmask), _ptr(self.scalars_in), stream))
+            tail_launches.append(self._cells_and_tail(batch, cg, True, stream, step_dev=self.step_dev))
             if self.peers is not None:
-                eng.fwdbwd_allreduce(batch, self.globals, self.zmask, self.packed, cg, self.peers)
                 self.peers.seq -= 1      # bookkeeping happens in graph_step
-            else:
-                eng.fwdbwd_packed(batch, self.globals, self.zmask, self.packed, cg)
-                if m.dist_group is not None:
-                    torch.distributed.all_reduce(self.packed, group=m.dist_group)
-            with torch.cuda.device(self.dev):
-                _lib.check(self.lib.cytof_global_bwd_adam_f64(
-                    C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
-                    _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
-                    _ptr(self.step_dev), _ptr(self.flag), C.c_int32(1), stream))
 
-        self._graph_launches = 2 + self._global_launches + (1 if idx_buf is not None else 0)
+        tail_launches = []
+        self._graph_launches = 0
         self._graph_idx = idx_buf
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
+        self._graph_launches = self._fwd_launches + tail_launches[0] + (1 if idx_buf is not None else 0)
         self.graph_multi, self._repeat = None, int(repeat)
         if self._repeat > 1:
             self.hist = torch.zeros((self._repeat, 5), dtype=F64, device=self.dev)
@@ -372,5 +370,7 @@ class FusedStep:
                 C.byref(g), _ptr(self.theta), _ptr(self.stash), _ptr(self.packed), _ptr(self.scalars_in),
                 _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grad), _ptr(self.scalars),
                 _ptr(None), _ptr(self.flag), C.c_int32(1 if update else 0), stream))
+        if self.peers is not None:
+            self.peers.seq += 1     # no exchange through the mailboxes in this step: keep the sequence in lock step with t
         self.launches += 2 * I + self._global_launches
         return self.scalars

@@ -94,6 +94,15 @@ def step_schedule(max_iter, backup_every, trace_every, chunk):
     return out
 
 
+def check_exchange(scrubbed):
+    """Code 2 in the scrub slot of a fused step = the peer-memory exchange of the packed gradient block gave up on
+    this or another rank (a rank died or stalled for ~2 s).  Nothing was updated; every rank sees the same code from
+    that step on, so all of them stop here instead of training on as diverged replicas."""
+    if scrubbed == 2.0:
+        raise RuntimeError('cytofpy_b200: the multi-GPU exchange of the gradient block timed out (a rank stalled or '
+                           'died); no update was applied on any rank from that step on')
+
+
 def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=10, seed=1,
         y_mean_init=-3.0, y_sd_init=0.1, trace_every=None, eps_conv=1e-6, tau=0.1,
         backup_every=10, y_quantiles=[0, 35, 70], p_bounds=[.05, .8, .05], scale=1,
@@ -177,6 +186,7 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
             rows = stepper.graph_steps().tolist()                 # one launch, one read-back per chunk
             stop = False
             for j, (elbo_t, ll, lp, lq, scrubbed) in enumerate(rows):
+                check_exchange(scrubbed)
                 if scrubbed != 0.0:
                     print("WARNING: Setting a nan gradient to zero!")
                 if finish(t + j, elbo_t, ll, lp, lq, scrubbed != 0.0):
@@ -196,6 +206,7 @@ def fit(y, minibatch_size=500, priors=None, max_iter=1000, lr=1e-1, print_freq=1
         if stepper is not None:
             out_t = stepper.graph_step() if replay else stepper.step(idx)
             elbo_t, ll, lp, lq, scrubbed = out_t.tolist()     # one 40-byte read-back
+            check_exchange(scrubbed)
             fixed_grad = scrubbed != 0.0
             if fixed_grad:
                 print("WARNING: Setting a nan gradient to zero!")

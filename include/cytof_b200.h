@@ -124,7 +124,10 @@ int cytof_elbo_fwdbwd_packed(const cytof_desc* d, const float* y, const int32_t*
  *   cytof_ipc_open_handle     maps a peer's mailbox (enables peer access lazily); cytof_ipc_close
  *   cytof_elbo_fwdbwd_allreduce   = cytof_elbo_fwdbwd_packed, but `packed` receives the SUM over
  *                             ranks; peer->seq must be 1, 2, 3, ... on every rank in lock step.
- * A wait that exceeds ~2 s (a dead peer) fills `packed` with NaN instead of hanging the GPU. */
+ * A wait that exceeds ~2 s (a dead peer) fills `packed` with NaN instead of hanging the GPU, and raises an abort
+ * word in EVERY rank's mailbox: from then on all ranks get NaN with +inf in the ll slot, which
+ * cytof_global_bwd_adam_f64 reads as "the exchange failed" (no update, out_scalars[4] = 2), so the replicas fail
+ * together instead of diverging.  The words are cleared by cytof_peer_alloc. */
 #define CYTOF_MAX_PEERS 16
 typedef struct cytof_peer_desc {
   int32_t world, rank;
@@ -219,7 +222,8 @@ int cytof_global_fwd_f64(const cytof_global_desc* g, const double* theta, const 
 
 /* Backward of the global part from packed (= output of cytof_elbo_fwdbwd_packed, summed over
  * ranks), loss scaling, NaN scrub (sets *flag), Adam update of theta when do_update != 0.
- * grad_out (nullable): d loss / d theta.  out_scalars[5] = elbo, ll, lp, lq, scrubbed (0/1). */
+ * grad_out (nullable): d loss / d theta.  out_scalars[5] = elbo, ll, lp, lq, scrubbed (0 / 1; 2 = `packed`
+ * carries the failed-exchange mark of cytof_elbo_fwdbwd_allreduce: nothing was updated, elbo .. lq are NaN). */
 int cytof_global_bwd_adam_f64(const cytof_global_desc* g, double* theta, double* stash,
                               const double* packed, const double* scalars_in, double* adam_m,
                               double* adam_v, double* grad_out, double* out_scalars,

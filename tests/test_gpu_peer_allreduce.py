@@ -153,3 +153,61 @@ def test_fused_peer_allreduce_two_ranks(tmp_path):
             assert rel(o[k], ref[k]) < 1e-4, k
     for k in outs[0].files:      # identical on both ranks, bit for bit
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def _stalled_worker(rank, world, port, out_dir):
+    """rank 1 stalls on the host for longer than the exchange's ~2 s bound: rank 0 must give up, and BOTH ranks must
+    report the failure code (no update, NaN results) instead of one of them training on alone"""
+    import time
+    import cytofpy_b200 as cy
+    from cytofpy_b200.model.fused import FusedStep
+    from cytofpy_b200.model.train import check_exchange
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    c = Case(CASE)
+    lo = [n * rank // world for n in c.N]
+    hi = [n * (rank + 1) // world for n in c.N]
+    y = [t[a:b].clone() for t, a, b in zip(c.y, lo, hi)]
+    pri = cy.model.default_priors(c.y, K=c.K, L=[c.L0, c.L1], y_bounds=[-5., -3.5, -2.])
+    torch.manual_seed(5)
+    mod = cy.model.Model(y=y, priors=pri, tau=c.tau, verbose=-1, use_stick_break=c.stick, model_noisy=c.noisy,
+                         scale=c.scale, device=dev, noise='philox', seed=9, N_global=c.N, row_global=lo,
+                         dist_group=dist.group.WORLD)
+    fs = FusedStep(mod, lr=0.05, seed=9, allreduce='peer')
+    idx = [np.arange(b - a) for a, b in zip(lo, hi)]
+    good = fs.step(idx).tolist()                 # a normal step first: the exchange works
+    torch.cuda.synchronize()
+    theta1 = fs.theta.clone()
+    dist.barrier()
+    if rank == 1:
+        time.sleep(3.5)                          # no GPU work is queued by this rank while rank 0 waits
+    bad = fs.step(idx).tolist()
+    torch.cuda.synchronize()
+    later = fs.step(idx).tolist()                # sticky: every later step of every rank fails the same way
+    raised = False
+    try:
+        check_exchange(later[4])
+    except RuntimeError:
+        raised = True
+    np.savez(os.path.join(out_dir, 'stall_rank%d.npz' % rank), good=np.array(good), bad=np.array(bad),
+             later=np.array(later), same=np.array([float(torch.equal(fs.theta, theta1))]), raised=np.array([float(raised)]))
+    dist.barrier()
+    fs.peers.close()
+    dist.destroy_process_group()
+
+
+def test_stalled_peer_poisons_every_rank(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    world = 2
+    mp.spawn(_stalled_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        o = np.load(os.path.join(str(tmp_path), 'stall_rank%d.npz' % r))
+        assert np.isfinite(o['good']).all() and o['good'][4] in (0.0, 1.0)
+        for key in ('bad', 'later'):
+            assert o[key][4] == 2.0, (r, key, o[key])
+            assert np.isnan(o[key][0]) and np.isnan(o[key][1])
+        assert o['same'][0] == 1.0          # no Adam update was applied from the failed exchange on
+        assert o['raised'][0] == 1.0
