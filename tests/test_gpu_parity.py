@@ -42,6 +42,10 @@ def pack_zmask(Z):
 
 
 def check_block(blk, ref, lay, tol=GRAD_TOL):
+    """Section-wise max-norm comparison.  A section whose reference is below 1e-25 is only required to be ~0: at a
+    fresh initialisation with J = 32 the quiet / noisy responsibility rho is ~1e-75 (fine in fp64, flushed to 0 in fp32;
+    SURVEY H2), so fixtures a, d, g test almost nothing of the LIKELIHOOD gradient through this function -- that is
+    the job of the trained fixtures b, c, f, h, i, j, k, l (mixed or unit rho) and of the full-size oracle tests."""
     for n in SECTIONS:
         a, b = blk[lay[n][0]:lay[n][0] + lay[n][1]], ref[lay[n][0]:lay[n][0] + lay[n][1]]
         if np.max(np.abs(b)) < 1e-25:

@@ -89,6 +89,65 @@ def test_sampler_is_roughly_uniform_and_full_batch_is_identity():
     assert np.array_equal(full.cpu().numpy(), np.arange(N))
 
 
+def test_sampler_pair_cooccurrence_and_positions():
+    """Second-order checks of the keyed Feistel sampler: over many steps every PAIR of indices must land in the same
+    minibatch about as often as under uniform sampling without replacement (a weak mixing function shows up here
+    long before it shows in the marginals), and the position of an index inside the minibatch must be uniform too
+    (the kernel walks consecutive minibatch rows, so position bias would correlate neighbours)."""
+    dev = torch.device('cuda', 0)
+    lib = _lib.load()
+    N, m, steps = 60, 12, 6000
+    out = torch.empty(m, dtype=torch.int32, device=dev)
+    co = np.zeros((N, N))
+    pos = np.zeros((N, m))
+    for step in range(steps):
+        _lib.check(lib.cytof_sample_minibatch(N, m, 11, step, 2, _p(out), C.c_void_p(0)))
+        a = out.cpu().numpy()
+        ind = np.zeros(N)
+        ind[a] = 1
+        co += np.outer(ind, ind)
+        pos[a, np.arange(m)] += 1
+    # P(i and j together) = m (m-1) / (N (N-1)) = 0.0373 -> 223.7 expected, binomial sd 14.7
+    off = co[~np.eye(N, dtype=bool)]
+    expect = steps * m * (m - 1) / (N * (N - 1))
+    sd = np.sqrt(expect * (1 - expect / steps))
+    assert abs(off.mean() - expect) < 1e-9                       # exact: every draw has m (m - 1) ordered pairs
+    assert off.min() > expect - 6 * sd and off.max() < expect + 6 * sd, (off.min(), off.max(), expect, sd)
+    z = (off - expect) / sd
+    assert 0.8 < z.std() < 1.2, z.std()                          # neither clumped nor suspiciously regular
+    # position uniformity: each (index, position) cell expects steps / N = 100 hits, sd ~ 9.9
+    e2 = steps / N
+    assert pos.min() > e2 - 6 * np.sqrt(e2) and pos.max() < e2 + 6 * np.sqrt(e2), (pos.min(), pos.max())
+
+
+def test_fit_with_the_reference_numpy_sampler_stream():
+    """sampler='numpy' keeps the reference's np.random.choice minibatch stream on the host (fit.py:96-102): the
+    minibatches fit draws are exactly the reference's for the same seed, and the fit trains."""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    N = [300, 100, 200]
+    y = cy.util.simdata(N=N, J=8, a_W=[100.] * 5, L0=3, L1=3)['data']['y']
+    pri = cy.model.default_priors(y, K=10, L=[3, 3], y_bounds=[-5., -3.5, -2.])
+    drawn = []
+    orig = np.random.choice
+
+    def spy(n, size, replace):
+        r = orig(n, size, replace=replace)
+        drawn.append(np.array(r))
+        return r
+    np.random.choice = spy
+    try:
+        out = cy.model.fit(y, max_iter=6, lr=1e-1, print_freq=100, eps_conv=0, priors=pri, minibatch_size=50, tau=0.1,
+                           trace_every=50, backup_every=50, verbose=0, seed=7, sampler='numpy')
+    finally:
+        np.random.choice = orig
+    assert len(out['elbo']) == 7 and np.isfinite(out['elbo']).all()
+    # what the reference's loop draws for seed 7: np.random.seed(seed) at the top of fit, then per step and sample
+    np.random.seed(7)
+    expect = [orig(n, 50, replace=False) for _ in range(7) for n in N]
+    assert len(drawn) == len(expect) and all(np.array_equal(a, b) for a, b in zip(drawn, expect))
+
+
 def test_fit_runs_and_improves_elbo(capsys):
     """the reference's own smoke test (tests/test_model.py:12-43) against the drop-in, with an
     assertion the reference lacks: the ELBO must improve."""
