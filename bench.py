@@ -306,6 +306,11 @@ def run_ours(args, w, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     step_ms, launches, clocks = timed_steps(job, args, dev, flush, barrier, local_rank)
+    exchange = None
+    if fs.peers is not None:      # where the last step's fused exchange spent its time on this rank (CTA 0, globaltimer)
+        tl = fs.peers.timeline()
+        exchange = {'own_part_stored_us': (tl[1] - tl[0]) / 1e3, 'wait_for_peers_us': (tl[2] - tl[1]) / 1e3,
+                    'sum_over_ranks_us': (tl[3] - tl[2]) / 1e3, 'rank': rank}
 
     fs.release_graph()
     # ---- dominant kernel alone (CUDA events on the launching stream, L2 flushed)
@@ -449,6 +454,8 @@ def run_ours(args, w, rank, world, local_rank):
                          'kernel_cells_per_s': cells_step / (k_ms * 1e-3)},
             'cpu_baseline': cpu,
         }
+        if exchange is not None:
+            out['exchange_last_step'] = exchange
         if other is not None:
             out[other] = {'scaling': other, 'value': other_cells * world / (other_ms * 1e-3), 'unit': UNIT,
                           'ms_per_step': other_ms, 'cells_total': other_cells * world,

@@ -70,6 +70,7 @@ _PROTOS = {
     'cytof_ipc_get_handle': (C.c_int, [_P, C.c_char_p]),
     'cytof_ipc_open_handle': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     'cytof_ipc_close': (C.c_int, [_P]),
+    'cytof_peer_debug': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'cytof_elbo_fwdbwd_allreduce': (C.c_int, [C.POINTER(Desc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
                                               C.POINTER(PeerDesc), _P]),
     'cytof_global_sizes': (C.c_int, [C.POINTER(GlobalDesc), C.POINTER(C.c_int64)]),

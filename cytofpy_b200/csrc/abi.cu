@@ -244,6 +244,12 @@ int cytof_ipc_close(void* ptr) {
   if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
   return CYTOF_OK;
 }
+int cytof_peer_debug(const void* mailbox, uint64_t out[4]) {
+  if (!mailbox || !out) return CYTOF_EINVAL;
+  const cudaError_t e = cudaMemcpy(out, static_cast<const unsigned char*>(mailbox) + 192, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { set_cuda_err(e); return CYTOF_ECUDA; }
+  return CYTOF_OK;
+}
 int cytof_elbo_fwdbwd_allreduce(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                                 const float* globals, const uint64_t* zmask, double* packed,
                                 void* workspace, size_t workspace_bytes_, const cytof_peer_desc* peer,

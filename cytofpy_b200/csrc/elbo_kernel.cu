@@ -457,6 +457,7 @@ constexpr int kFinLanes = CYTOF_FIN_LANES;     // 8, 16 or 32 lanes per output
 //   [132, 136)  uint32 error: set when a wait of THIS rank timed out (sticky until the mailbox is freed)
 //   [136, 140)  uint32 abort: set by ANY rank whose wait timed out (it stores it into every mailbox), so that all
 //               ranks poison their results and raise together instead of diverging silently
+//   [192, 224)  uint64 ns time stamps of CTA 0 in the last step: entry, own part stored, flags seen, sum done
 //   [256, ...)  double slots[parity][src][nout]: the packed vector of rank `src` for steps of that parity
 // Step s: every finalise thread stores its output straight into slot [s & 1][rank] of EVERY mailbox
 // (its own included); the last CTA of the grid publishes flags[rank] = s to every peer with a
@@ -468,6 +469,7 @@ struct PeerArgs {
   unsigned long long seq;
   const long long* seq_dev;    // non-null: seq = *seq_dev + 1
   int nout;
+  int all_ctas;                // every CTA waits for the flags and sums its own outputs (grid co-resident), else the last CTA does
   unsigned char* mailbox[CYTOF_MAX_PEERS];
 };
 constexpr size_t kPeerHeaderBytes = 256;
@@ -592,28 +594,64 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   unsigned* ticket = reinterpret_cast<unsigned*>(mine + 128);
   unsigned* errw = reinterpret_cast<unsigned*>(mine + 132);
   volatile unsigned* abortw = reinterpret_cast<volatile unsigned*>(mine + 136);
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(mine + 192);    // [4] ns time stamps of CTA 0 (cytof_peer_debug)
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  auto now_ns = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  if (stamp) dbg[0] = now_ns();
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
   __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if ((int)threadIdx.x < peer.world) {
-    if (threadIdx.x == 0) *ticket = 0u;
-    st_release_sys(reinterpret_cast<unsigned long long*>(peer.mailbox[threadIdx.x]) + peer.rank, seq);
-    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < seq) {
-      if (*abortw != 0u) break;                                    // another rank gave up: do not wait out the 2 s
-      if (clock64() - t0 > 4000000000ll) {                         // ~2 s: a peer died; never hang the GPU
-        *errw = 1u;
-        for (int q = 0; q < peer.world; ++q) *reinterpret_cast<volatile unsigned*>(peer.mailbox[q] + 136) = 1u;
-        __threadfence_system();
-        break;
+  // bounded, abort-aware wait of thread q < world for the flag of rank q in this rank's mailbox
+  auto wait_flags = [&]() {
+    if ((int)threadIdx.x < peer.world) {
+      const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < seq) {
+        if (*abortw != 0u) break;                                    // another rank gave up: do not wait out the 2 s
+        if (clock64() - t0 > 4000000000ll) {                         // ~2 s: a peer died; never hang the GPU
+          *errw = 1u;
+          for (int q = 0; q < peer.world; ++q) *reinterpret_cast<volatile unsigned*>(peer.mailbox[q] + 136) = 1u;
+          __threadfence_system();
+          break;
+        }
+        __nanosleep(64);
       }
     }
-  }
-  __syncthreads();
-  const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u || *abortw != 0u;
+    __syncthreads();
+  };
   const double* slots = reinterpret_cast<const double*>(mine + kPeerHeaderBytes) + (size_t)par * peer.world * peer.nout;
+  const double kNaN = __longlong_as_double(0x7ff8000000000000ll), kInf = __longlong_as_double(0x7ff0000000000000ll);
+  if (s_last) {      // this rank's vector is complete in every mailbox: publish the sequence number to every peer
+    __threadfence_system();
+    if ((int)threadIdx.x < peer.world) {
+      if (threadIdx.x == 0) *ticket = 0u;
+      st_release_sys(reinterpret_cast<unsigned long long*>(peer.mailbox[threadIdx.x]) + peer.rank, seq);
+    }
+  }
+  if (peer.all_ctas) {
+    // ---- every CTA of the (co-resident) grid waits for the world flags itself and sums ITS outputs over the
+    // world slots in rank order: no serial tail in one CTA (with 8 ranks that tail read 36 k doubles from 256 threads)
+    if (stamp) dbg[1] = now_ns();
+    wait_flags();
+    if (stamp) dbg[2] = now_ns();
+    const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u || *abortw != 0u;
+    if (live && sub == 0) {
+      double v[CYTOF_MAX_PEERS];
+#pragma unroll
+      for (int q = 0; q < CYTOF_MAX_PEERS; ++q) v[q] = q < peer.world ? __ldcg(slots + (size_t)q * peer.nout + t) : 0.0;
+      double a = 0.0;
+#pragma unroll
+      for (int q = 0; q < CYTOF_MAX_PEERS; ++q) a += v[q];
+      if (bad) a = (t == peer.nout - 2) ? kInf : kNaN;      // +inf in the ll slot: the mark global_adam_body reads as "the exchange failed"
+      packed[t] = a;
+    }
+    if (stamp) dbg[3] = now_ns();
+    return;
+  }
+  if (!s_last) return;
+  if (stamp) dbg[1] = now_ns();
+  wait_flags();
+  if (stamp) dbg[2] = now_ns();
+  const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u || *abortw != 0u;
   // one CTA sums world x nout doubles: all loads of two outputs (up to 32) are issued before the first add,
   // otherwise this tail is a chain of L2 round trips; the sum runs in rank order on every rank (x + 0.0 = x)
   for (int o = threadIdx.x; o < peer.nout; o += 2 * blockDim.x) {
@@ -627,9 +665,9 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     double a = 0.0, c = 0.0;
 #pragma unroll
     for (int q = 0; q < CYTOF_MAX_PEERS; ++q) { a += v[q]; c += w[q]; }
-    if (bad) {      // NaN everywhere, +inf in the ll slot: the mark global_adam_body reads as "the exchange failed"
-      a = (o == peer.nout - 2) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0x7ff8000000000000ll);
-      c = (o2 == peer.nout - 2) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0x7ff8000000000000ll);
+    if (bad) {
+      a = (o == peer.nout - 2) ? kInf : kNaN;
+      c = (o2 == peer.nout - 2) ? kInf : kNaN;
     }
     packed[o] = a;
     if (o2 < peer.nout) packed[o2] = c;
@@ -906,6 +944,9 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     pa.seq = peer->seq;
     pa.seq_dev = reinterpret_cast<const long long*>(peer->seq_dev);
     pa.nout = nout;
+    // all finalise CTAs co-resident (8 x 256 threads per SM): each of them may wait for the peers' flags
+    static const bool serial_sum = [] { const char* e = getenv("CYTOF_PEER_SERIAL_SUM"); return e && e[0] == '1'; }();
+    pa.all_ctas = !serial_sum && (nout * kFinLanes + 255) / 256 <= device_sm_count() * 8;
     for (int q = 0; q < peer->world; ++q) pa.mailbox[q] = static_cast<unsigned char*>(peer->mailbox[q]);
   }
   *err = launch_pdl(elbo_finalize_kernel, dim3((nout * kFinLanes + 255) / 256), dim3(256), 0, stream, p, grad_block, ll_lqy,

@@ -71,6 +71,15 @@ class PeerMailboxes:
         self.desc.seq = self.seq
         return self.desc
 
+    def timeline(self):
+        """ns stamps CTA 0 of the last exchange left in this rank's mailbox: (entry, own part stored, all flags seen,
+        sum done) -- the split of the exchange cost that bench.py reports for N > 1"""
+        out = (C.c_uint64 * 4)()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.cytof_peer_debug(C.c_void_p(self.ptrs[self.rank]), out))
+        return [int(v) for v in out]
+
     def close(self):
         if not self.ptrs:
             return

@@ -141,6 +141,9 @@ int cytof_peer_free(void* ptr);
 int cytof_ipc_get_handle(void* ptr, unsigned char handle[64]);
 int cytof_ipc_open_handle(const unsigned char handle[64], void** ptr);
 int cytof_ipc_close(void* ptr);
+/* Debug: globaltimer (ns) stamps CTA 0 of the last exchange left in the OWN mailbox: kernel entry, own outputs
+ * stored, all flags seen, sum done.  Synchronous copy; call after the stream has drained. */
+int cytof_peer_debug(const void* mailbox, uint64_t out[4]);
 int cytof_elbo_fwdbwd_allreduce(const cytof_desc* d, const float* y, const int32_t* idx, const float* eps,
                                 const float* globals, const uint64_t* zmask, double* packed,
                                 void* workspace, size_t workspace_bytes, const cytof_peer_desc* peer,
