@@ -115,7 +115,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.001)
+                time.sleep(0.0002)
         except Exception as e:  # NVML missing: report it, do not fake numbers
             self.reasons.add('nvml_unavailable:%s' % type(e).__name__)
         self.ready.set()
@@ -275,9 +275,26 @@ def timed_steps(job, args, dev, flush, barrier, local_rank):
         one_step(args.warmup + t)
         ev[t][1].record()
     barrier()
-    sampler.stop_flag = True
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    return step_ms, fs.launches - launches0, sampler.summary()      # graph_step counts the sampler kernels itself
+    launches = fs.launches - launches0      # graph_step counts the sampler kernels itself
+    # NVML answers in milliseconds; K short steps can end before its first sample.  Keep running the SAME step
+    # (untimed, the same number on every rank) until the region under load has lasted ~50 ms, so that `clocks`
+    # always holds samples taken while these kernels run
+    est = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(est, op=torch.distributed.ReduceOp.MAX)
+    est = max(float(est.item()), 1e-3)
+    n_extra = 0 if args.steps * est >= 50.0 else min(20000, int(50.0 / est) + 1)
+    for t in range(n_extra):
+        one_step(args.warmup + args.steps + t)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(2.0)
+    clocks = sampler.summary()
+    clocks['note'] = 'NVML samples over the K timed steps' + (
+        ' and %d further untimed replays of the same step (K steps last %.1f ms, less than one NVML round trip)'
+        % (n_extra, args.steps * est) if n_extra else '')
+    return step_ms, launches, clocks
 
 
 def run_ours(args, w, rank, world, local_rank):
