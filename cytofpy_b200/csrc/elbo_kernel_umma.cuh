@@ -1,7 +1,13 @@
-// CTA-wide, warp-specialised Blackwell kernel for J <= 32, K <= 32 (BASELINE cfg1-cfg4): the successor of
-// elbo_kernel_mma.cuh.  ncu on that kernel (profiles/README.md, r1e) showed four schedulers at 55 % issue with
+// CTA-wide, warp-specialised Blackwell kernel for J <= 32, K <= 32 (BASELINE cfg1-cfg4): the tcgen05 / TMEM / bulk-copy
+// form of elbo_kernel_mma.cuh.  OPT-IN (CYTOF_UMMA=1): it passes the same parity suite (tests/test_gpu_umma_variant.py)
+// and measures 1.8x SLOWER than the per-warp kernel (0.486 vs 0.267 ms per 1 M cells at cfg4) -- tcgen05.ld moves
+// 32 B/clk/SM, SS-mode MMAs stream their operands from shared memory at 128 B/clk, and the forward -> backward round
+// trip through the issuers and the cell warps is ~5,000 cycles against a TMEM stash of four quarters
+// (profiles/README.md, round 2).
+//
+// Why it was built: ncu on the per-warp kernel (profiles/README.md, r1e) showed four schedulers at 55 % issue with
 // two 254-register warps each; the per-warp mma.sync contractions (7 HMMA + LDSM + fragment splits + ~18 LDS/STS
-// per cell, a ~1,000-cycle dependent chain per tile) sat on the same schedulers as the MUFU / FMA work.  Here
+// per cell, a ~1,000-cycle dependent chain per tile) sit on the same schedulers as the MUFU / FMA work.  Here
 //   * the three J x K contractions of Model.py:246-249 (+ autograd twins) are tcgen05.mma.kind::tf32 with M = 128,
 //     N = 32, issued by ONE thread each, operands in shared memory, accumulators in tensor memory:
 //         f   [n, k]  = A1[n, :] . Z[:, k] + N0[n, :] . (Z[:, k] - 1)            (N0 = -A0; rows = cells)
