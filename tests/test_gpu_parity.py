@@ -268,6 +268,10 @@ def test_philox_mode_matches_oracle_on_emitted_noise_and_is_shard_invariant():
     # imputed matrix from the emit kernel
     y_imp = eng.impute(batch, G).cpu().numpy()
     assert np.allclose(y_imp, np.concatenate(y_imp_ref), rtol=2e-6, atol=2e-6)
+    # row r of DIFFERENT samples gets independent draws (the sample index is part of the Philox counter; the
+    # reference draws a dense normal per sample, vae.py:33): same rows 0..499 of sample 0 and of sample 1
+    a, b = eps[:500], eps[N[0]:N[0] + 500]
+    assert not np.array_equal(a, b) and abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 0.02
     # a different step gives different draws; the same step the same draws
     assert not np.allclose(eng.philox_noise(Batch(N, None, None, step=8)).cpu().numpy(), eps)
     assert np.array_equal(eng.philox_noise(Batch(N, None, None, step=7)).cpu().numpy(), eps.astype(np.float32))
