@@ -454,3 +454,53 @@ def test_full_size_fp64_oracle_cfg4(noisy):
         frac = dl / np.array(N)
         assert (frac > 0.02).all() and (frac < 0.98).all(), frac
     check_block(blk, blk_ref, lay)
+
+
+def test_full_size_fp64_oracle_cfg5_shape():
+    """BASELINE cfg5 shapes (J = 40, K = 50, L = 8/8: the tensor-core kernel with dZ in tensor memory) on
+    8 x 25,000 cells in one launch against the fp64 oracle over the same 200,000 cells."""
+    I, J, K, L0, L1 = 8, 40, 50, 8, 8
+    N = [25000] * I
+    dev = _dev()
+    s = cy.util.synth_cytof(N, J, [100.] * 5, L0, L1, seed=2)
+    _, g = _random_problem(I, J, K, L0, L1, [1] * I, 0.0, seed=41)
+    g['mu0'], g['mu1'] = -(np.arange(L0) * 0.7 + 1.5), np.arange(L1) * 0.7 + 1.5
+    g['sig'], g['eps'], noisy_sd = np.linspace(1.25, 1.35, I), np.full(I, 0.01), 1.8
+    y64 = [a.astype(np.float64) for a in s['y']]
+    ll_ref, _, blk_ref = _oracle_whole_matrix(y64, N, g, True, noisy_sd)
+    eng = CellEngine([torch.from_numpy(a) for a in s['y']], dev, K, L0, L1, True, noisy_sd, 1.0, g['b'], seed=9)
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    blk, ll = eng.fwdbwd(Batch(N, None, None, step=1), G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy().copy()
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref), (ll[0], ll_ref)
+    check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
+
+
+def test_full_size_missing_data_with_in_kernel_noise():
+    """cfg4 shapes with ~30 % of the negative entries missing, 8 x 25,000 cells, IN-KERNEL Philox noise (the staged
+    pre-pass of full-batch tiles): the draws the kernel uses are emitted by cytof_noise_emit_f32 and handed to the fp64
+    oracle, which then has to reproduce ll, log_qy and every gradient section incl. the imputation parameters."""
+    I, J, K, L0, L1 = 8, 32, 30, 5, 5
+    N = [25000] * I
+    dev = _dev()
+    s = cy.util.synth_cytof(N, J, [100.] * 5, L0, L1, seed=3)
+    beta = cy.model.solve_beta([-5., -3.5, -2.], [.05, .8, .05]).numpy()
+    cy.util.inject_missing(s['y'], beta, rate=0.3, seed=4)
+    assert all(np.isnan(a).mean() > 0.05 for a in s['y'])
+    _, g = _random_problem(I, J, K, L0, L1, [1] * I, 0.0, seed=51)
+    g['mu0'], g['mu1'] = -(np.arange(L0) + 1.5), np.arange(L1) + 1.5
+    g['sig'], g['eps'], noisy_sd = np.linspace(1.25, 1.35, I), np.full(I, 0.01), 1.8
+    g['b'] = np.tile(beta, (I, 1))
+    eng = CellEngine([torch.from_numpy(a) for a in s['y']], dev, K, L0, L1, True, noisy_sd, 0.7, g['b'], seed=21)
+    assert not eng.no_missing
+    batch = Batch(N, None, None, step=5)
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    blk, ll = eng.fwdbwd(batch, G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy().copy()
+    eps = eng.philox_noise(batch).cpu().numpy().astype(np.float64)
+    eps_l = list(np.split(eps, np.cumsum(N)[:-1], axis=0))
+    y64 = [a.astype(np.float64) for a in s['y']]
+    ll_ref, lqy_ref, blk_ref = _oracle_whole_matrix(y64, N, g, True, noisy_sd, eps=eps_l, scale=0.7)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref), (ll[0], ll_ref)
+    assert abs(ll[1] - lqy_ref) <= ELBO_TOL * abs(lqy_ref), (ll[1], lqy_ref)
+    check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
