@@ -442,13 +442,24 @@ elbo_fwdbwd_kernel(const ElboParams p) {
   for (int t = threadIdx.x; t < pl.total; t += kThreads) out[t] = sred[t];
 }
 
-// kFinLanes threads per output of the gradient block (+ ll, log_qy): lane s sums the per-CTA
-// records s, s + kFinLanes, ... of the relevant sample(s) in fp64, the lanes are combined by a
-// fixed butterfly (=> reproducible for a given grid), then the per-sample scalings are applied.
-#ifndef CYTOF_FIN_LANES
-#define CYTOF_FIN_LANES 32
-#endif
-constexpr int kFinLanes = CYTOF_FIN_LANES;     // 8, 16 or 32 lanes per output
+// Finalise: the per-CTA partial records -> gradient block (+ ll, log_qy), fp64.  The records are [nblocks][pl.total]
+// floats, so the kernel walks them in RECORD space: a CTA owns 32 consecutive offsets of one section (lane = offset:
+// every load of a warp is one 128-byte line of one record), its 8 warps split the records of the section's range
+// (warp w: b0 + w, b0 + w + 8, ...), and warp 0 adds the 8 partial sums in warp order -- a fixed order for a given
+// grid, so the result is reproducible.  The handful of outputs that combine several sums with per-sample factors
+// (dmu, dsig, deps, ll, log_qy) take one warp each (lanes over records, butterfly).  ~150 CTAs at cfg4 instead of
+// one warp per output (570 CTAs reading one 32-byte sector per load).
+struct FinPlan { int per_sample, w_s0, w_s1, w_k, w_j, w_z, n_small, n_units, n_ctas; };
+__host__ __device__ inline FinPlan fin_plan(int I, int J, int K, int L0, int L1) {
+  FinPlan f;
+  f.w_s0 = (L0 * J + 31) / 32; f.w_s1 = (L1 * J + 31) / 32; f.w_k = (K + 31) / 32; f.w_j = (J + 31) / 32;
+  f.per_sample = f.w_s0 + f.w_s1 + f.w_k + 3 * f.w_j;
+  f.w_z = (J * K + 31) / 32;
+  f.n_small = L0 + L1 + 2 * I + 2;
+  f.n_units = I * f.per_sample + f.w_z;
+  f.n_ctas = f.n_units + (f.n_small + 7) / 8;
+  return f;
+}
 
 // One-shot all-reduce over NVLink / NVSwitch peer memory, fused into the finalise kernel.  Every
 // rank owns a mailbox (cudaMalloc'ed by cytof_peer_alloc, mapped into the peers with CUDA IPC):
@@ -483,93 +494,126 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
-                                     double* __restrict__ ll_lqy, double* __restrict__ packed,
-                                     const PeerArgs peer) {
+__global__ void __launch_bounds__(256)
+elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
+                     double* __restrict__ ll_lqy, double* __restrict__ packed,
+                     const PeerArgs peer) {
   pdl_enter();
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   const BlockLayout bl = block_layout(I, J, K, L0, L1);
   const PartialLayout pl = partial_layout(J, K, L0, L1);
   const GlobalsLayout gl = globals_layout(I, J, K, L0, L1);
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = gt / kFinLanes, sub = gt % kFinLanes;
-  const bool live = t < bl.total + 2;      // whole lane groups are live or not together
-  const unsigned gmask = kFinLanes >= 32 ? 0xffffffffu
-                                         : ((1u << (kFinLanes & 31)) - 1u) << ((threadIdx.x & 31) / kFinLanes * kFinLanes);
+  const FinPlan fp = fin_plan(I, J, K, L0, L1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* __restrict__ P = p.partials;
   const float* __restrict__ G = p.globals;
-  auto group_sum = [&](double a) -> double {
-#pragma unroll
-    for (int o = 1; o < kFinLanes; o <<= 1) a += __shfl_xor_sync(gmask, a, o);
-    return a;
-  };
-  auto sum_range = [&](int b0, int b1, int off) -> double {
-    // 4 independent loads in flight per lane, kFinLanes lanes (one warp) per output
+  __shared__ double s_part[8][32];
+  int t = -1;            // the output this thread owns (-1: none)
+  double r = 0.0;
+  const int unit = (int)blockIdx.x;
+  if (unit < fp.n_units) {
+    // ---- 32 consecutive record offsets of one section, records split over the 8 warps
+    int b0 = 0, b1 = p.nblocks, off = 0, len = 0, e = 0, kind = 6, i = 0;
+    if (unit < I * fp.per_sample) {
+      i = unit / fp.per_sample;
+      int q = unit % fp.per_sample;
+      b0 = p.blk_begin[i]; b1 = p.blk_begin[i + 1];
+      if (q < fp.w_s0) { kind = 0; off = pl.sw0; len = L0 * J; }
+      else if ((q -= fp.w_s0) < fp.w_s1) { kind = 1; off = pl.sw1; len = L1 * J; }
+      else if ((q -= fp.w_s1) < fp.w_k) { kind = 2; off = pl.gW; len = K; }
+      else if ((q -= fp.w_k) < fp.w_j) { kind = 3; off = pl.dvm; len = J; }
+      else if ((q -= fp.w_j) < fp.w_j) { kind = 4; off = pl.dvls; len = J; }
+      else { q -= fp.w_j; kind = 5; off = pl.nm; len = J; }
+      e = 32 * q + lane;
+    } else {
+      off = pl.dZ; len = J * K;
+      e = 32 * (unit - I * fp.per_sample) + lane;
+    }
+    const bool valid = e < len;
+    const float* src = P + off + (valid ? e : 0);
     double a = 0.0;
-    int b = b0 + sub;
-    for (; b + 3 * kFinLanes < b1; b += 4 * kFinLanes) {
+    int b = b0 + warp;
+    for (; b + 24 < b1; b += 32) {           // 4 independent loads in flight
       float v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(P + (size_t)(b + u * kFinLanes) * pl.total + off);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(b + 8 * u) * pl.total);
 #pragma unroll
       for (int u = 0; u < 4; ++u) a += (double)v[u];
     }
-    for (; b < b1; b += kFinLanes) a += (double)__ldg(P + (size_t)b * pl.total + off);
-    return group_sum(a);
-  };
-  auto sum_sample = [&](int i, int off) -> double { return sum_range(p.blk_begin[i], p.blk_begin[i + 1], off); };
-  double r = 0.0;
-  if (!live) {
-  } else if (t >= bl.total) {  // ll, log_qy
-    const int which = t - bl.total;
-    double a = 0.0;
-    for (int b = sub; b < p.nblocks; b += kFinLanes)
-      a += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
-    r = group_sum(a);
-  } else if (t < bl.dmu1) {  // dmu0[l] = sum_i (1/sig_i^2) sum w d
-    const int l = t - bl.dmu0;
-    for (int i = 0; i < I; ++i) {
-      const double s = (double)G[gl.sig + i];
-      r += sum_sample(i, pl.swd0 + l) / (s * s);
+    for (; b < b1; b += 8) a += (double)__ldg(src + (size_t)b * pl.total);
+    s_part[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0 && valid) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) r += s_part[w][lane];
+      switch (kind) {
+        case 0: t = bl.dle0 + (i * J + e % J) * L0 + e / J; break;               // e = l J + j
+        case 1: t = bl.dle1 + (i * J + e % J) * L1 + e / J; break;
+        case 2: t = bl.dlw + i * K + e; break;
+        case 3: t = bl.dvm + i * J + e; break;
+        case 4: t = bl.dvls + i * J + e; break;
+        case 5: t = bl.dlq + i * J + e; r *= -(double)p.fac[i] * (double)p.scale; break;   // d log_qy / d vls = -fac scale #missing
+        default: t = bl.dZ + (e % J) * K + e / J; r *= 0.6931471805599453; break;  // e = k J + j; dZ_jk = ln2 sum g_k D2_j
+      }
     }
-  } else if (t < bl.dsig) {
-    const int l = t - bl.dmu1;
-    for (int i = 0; i < I; ++i) {
-      const double s = (double)G[gl.sig + i];
-      r += sum_sample(i, pl.swd1 + l) / (s * s);
+  } else {
+    // ---- outputs that mix several sums: one warp each, lanes over the records.  Every lane issues all its loads
+    // (records x up to two offsets, and the per-sample factor) before the first add: ONE memory round trip per output
+    const int sidx = (unit - fp.n_units) * 8 + warp;
+    auto butterfly = [&](double a) -> double {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      return a;
+    };
+    if (sidx < fp.n_small) {
+      if (sidx < L0 + L1) {             // dmu_z[l] = sum_i (1/sig_i^2) sum_b (sum w d)_b
+        const bool z1 = sidx >= L0;
+        const int l = z1 ? sidx - L0 : sidx;
+        const int off = (z1 ? pl.swd1 : pl.swd0) + l;
+        int i = 0;
+        for (int bb = lane; bb < p.nblocks; bb += 128) {
+          float v[4], sg[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int b = bb + 32 * u;
+            const bool in = b < p.nblocks;
+            while (in && i + 1 < I && b >= p.blk_begin[i + 1]) ++i;
+            v[u] = in ? __ldg(P + (size_t)b * pl.total + off) : 0.f;
+            sg[u] = __ldg(G + gl.sig + i);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) r += (double)v[u] / ((double)sg[u] * (double)sg[u]);
+        }
+        r = butterfly(r);
+        t = (z1 ? bl.dmu1 : bl.dmu0) + l;
+      } else if (sidx < L0 + L1 + 2 * I) {
+        // dsig_i = sum w d^2 / sig^3 - (J sum fac rho) / sig;  deps_i = -sum fac rho/(1-eps) + sum fac (1-rho)/eps
+        const bool is_eps = sidx >= L0 + L1 + I;
+        const int i = sidx - L0 - L1 - (is_eps ? I : 0);
+        const int offa = pl.sc + (is_eps ? 2 : 0), offb = pl.sc + 1;
+        const double par = (double)__ldg(G + (is_eps ? gl.eps : gl.sig) + i);
+        double a = 0.0, c = 0.0;
+        for (int b = p.blk_begin[i] + lane; b < p.blk_begin[i + 1]; b += 32) {
+          a += (double)__ldg(P + (size_t)b * pl.total + offa);
+          c += (double)__ldg(P + (size_t)b * pl.total + offb);
+        }
+        a = butterfly(a);
+        c = butterfly(c);
+        if (is_eps) { r = p.model_noisy ? -c / (1.0 - par) + a / par : 0.0; t = bl.deps + i; }
+        else { r = a / (par * par * par) - (double)J * c / par; t = bl.dsig + i; }
+      } else {                          // ll, log_qy
+        const int which = sidx - (L0 + L1 + 2 * I);
+        for (int b = lane; b < p.nblocks; b += 32)
+          r += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
+        r = butterfly(r);
+        t = bl.total + which;
+      }
+      if (lane != 0) t = -1;
     }
-  } else if (t < bl.dle0) {  // dsig_i = sum w d^2 / sig^3 - (J sum fac rho) / sig
-    const int i = t - bl.dsig;
-    const double s = (double)G[gl.sig + i];
-    r = sum_sample(i, pl.sc + 0) / (s * s * s) - (double)J * sum_sample(i, pl.sc + 1) / s;
-  } else if (t < bl.dle1) {
-    const int q = t - bl.dle0, i = q / (J * L0), j = (q / L0) % J, l = q % L0;
-    r = sum_sample(i, pl.sw0 + l * J + j);
-  } else if (t < bl.dlw) {
-    const int q = t - bl.dle1, i = q / (J * L1), j = (q / L1) % J, l = q % L1;
-    r = sum_sample(i, pl.sw1 + l * J + j);
-  } else if (t < bl.dZ) {
-    const int q = t - bl.dlw, i = q / K, k = q % K;
-    r = sum_sample(i, pl.gW + k);
-  } else if (t < bl.deps) {  // dZ_jk = ln2 * sum g_k D2_j   (D2 in log2 units)
-    const int q = t - bl.dZ, j = q / K, k = q % K;
-    r = sum_range(0, p.nblocks, pl.dZ + k * J + j) * 0.6931471805599453;
-  } else if (t < bl.dvm) {  // deps_i = -sum fac rho/(1-eps) + sum fac (1-rho)/eps
-    const int i = t - bl.deps;
-    const double e = (double)G[gl.eps + i];
-    r = p.model_noisy ? -sum_sample(i, pl.sc + 1) / (1.0 - e) + sum_sample(i, pl.sc + 2) / e : 0.0;
-  } else if (t < bl.dvls) {
-    const int q = t - bl.dvm, i = q / J, j = q % J;
-    r = sum_sample(i, pl.dvm + j);
-  } else if (t < bl.dlq) {
-    const int q = t - bl.dvls, i = q / J, j = q % J;
-    r = sum_sample(i, pl.dvls + j);
-  } else {  // d log_qy / d vls_ij = -fac_i * scale * #missing
-    const int q = t - bl.dlq, i = q / J, j = q % J;
-    r = -(double)p.fac[i] * (double)p.scale * sum_sample(i, pl.nm + j);
   }
+  const bool owner = t >= 0;
   if (peer.world <= 1) {
-    if (live && sub == 0) {
+    if (owner) {
       if (t >= bl.total) {
         if (ll_lqy) ll_lqy[t - bl.total] = r;
       } else if (grad_block) {
@@ -583,8 +627,8 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
   const unsigned long long seq = peer.seq_dev ? (unsigned long long)(*peer.seq_dev + 1) : peer.seq;
   const int par = (int)(seq & 1ull);
   const size_t slot_off = kPeerHeaderBytes + ((size_t)par * peer.world + peer.rank) * (size_t)peer.nout * sizeof(double);
-  if (live) {     // the lanes of an output share the peers between them
-    for (int q = sub; q < peer.world; q += kFinLanes)
+  if (owner) {
+    for (int q = 0; q < peer.world; ++q)
       reinterpret_cast<double*>(peer.mailbox[q] + slot_off)[t] = r;
   }
   __threadfence_system();
@@ -634,7 +678,7 @@ __global__ void elbo_finalize_kernel(const ElboParams p, float* __restrict__ gra
     wait_flags();
     if (stamp) dbg[2] = now_ns();
     const bool bad = *reinterpret_cast<volatile unsigned*>(errw) != 0u || *abortw != 0u;
-    if (live && sub == 0) {
+    if (owner) {
       double v[CYTOF_MAX_PEERS];
 #pragma unroll
       for (int q = 0; q < CYTOF_MAX_PEERS; ++q) v[q] = q < peer.world ? __ldcg(slots + (size_t)q * peer.nout + t) : 0.0;
@@ -946,10 +990,10 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
     pa.nout = nout;
     // all finalise CTAs co-resident (8 x 256 threads per SM): each of them may wait for the peers' flags
     static const bool serial_sum = [] { const char* e = getenv("CYTOF_PEER_SERIAL_SUM"); return e && e[0] == '1'; }();
-    pa.all_ctas = !serial_sum && (nout * kFinLanes + 255) / 256 <= device_sm_count() * 8;
+    pa.all_ctas = !serial_sum && fin_plan(d->I, d->J, d->K, d->L0, d->L1).n_ctas <= device_sm_count() * 8;
     for (int q = 0; q < peer->world; ++q) pa.mailbox[q] = static_cast<unsigned char*>(peer->mailbox[q]);
   }
-  *err = launch_pdl(elbo_finalize_kernel, dim3((nout * kFinLanes + 255) / 256), dim3(256), 0, stream, p, grad_block, ll_lqy,
+  *err = launch_pdl(elbo_finalize_kernel, dim3(fin_plan(d->I, d->J, d->K, d->L0, d->L1).n_ctas), dim3(256), 0, stream, p, grad_block, ll_lqy,
                     packed, pa);
   return *err == cudaSuccess ? CYTOF_OK : CYTOF_ECUDA;
 }
