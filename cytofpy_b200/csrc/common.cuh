@@ -84,10 +84,12 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
   }
 }
 
-// Standard-normal draws for (global row, marker j) of step `step`.  One Philox4x32-10 block is
-// keyed by (global row / 4, marker) and yields FOUR normals (two Box-Muller pairs), one for each
-// of the 4 consecutive rows of the group: a warp that walks consecutive rows (full-batch tiles)
-// pays one Philox block per 4 cells.  Independent of how cells are split over warps, CTAs or GPUs.
+// Standard-normal draws for (position, marker j) of step `step`; position = row_global[i] + index of the cell in
+// the sample's batch -- the global row for full batches (independent of how the cells are split over warps, CTAs or
+// GPUs), the slot of the minibatch for gathered ones (the reference draws a dense (B_i, J) normal per step too,
+// vae.py:33; until round 2 gathered batches were keyed by the row, which cost one Philox block per cell).
+// One Philox4x32-10 block is keyed by (position / 4, marker) and yields FOUR normals (two Box-Muller pairs), one
+// for each of the 4 consecutive positions of the group: a warp that walks a tile pays one block per 4 cells.
 // Third counter word of the per-cell draws: marker | sample << 8, so that row r of different samples (every sample's
 // rows start at row_global[i], often 0) gets independent draws, as the reference's dense normal_ does (vae.py:33).
 __device__ __forceinline__ uint32_t philox_ctr(int j, int sample) { return (uint32_t)j | ((uint32_t)sample << 8); }

@@ -198,7 +198,7 @@ elbo_fwdbwd_kernel(const ElboParams p) {
           const int j = lane + 32 * jp;
           e[jp] = p.noise_mode == CYTOF_NOISE_EXTERNAL
                       ? (p.eps ? __ldg(p.eps + (cb + c) * J + j) : 0.f)
-                      : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)(row_cur - row_base), philox_ctr(j, i));
+                      : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)c, philox_ctr(j, i));   // keyed by the POSITION in the batch
           yv[jp] = fmaf(sd[jp], e[jp], vm[jp]);
         }
     }
@@ -733,7 +733,7 @@ __global__ void impute_emit_kernel(const ElboParams p, float* __restrict__ eps_o
   if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
     if (p.eps) e = p.eps[c * p.J + j];
   } else {
-    e = philox_normal(p.seed, elbo_step(p), (unsigned long long)(p.row_global[i] + lrow), philox_ctr(j, i));
+    e = philox_normal(p.seed, elbo_step(p), (unsigned long long)(p.row_global[i] + lc), philox_ctr(j, i));   // position, not row
   }
   if (eps_out) { eps_out[t] = e; return; }
   const GlobalsLayout gl = globals_layout(p.I, p.J, p.K, p.L0, p.L1);

@@ -190,7 +190,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   // that is a multiple of 8, so that the 8-cell tiles coincide with two 4-row Philox blocks (pre-pass)
   auto cut = [&](const long long q) -> long long {
     long long x = Bi * q / nb;
-    if (!HAS_IDX && q > 0 && q < nb) x -= (long long)((grow_base + (unsigned long long)x) & 7ull);
+    if (q > 0 && q < nb) x -= (long long)((grow_base + (unsigned long long)x) & 7ull);
     return x < 0 ? 0 : x;
   };
   const long long c_lo = cut(lb), c_hi = cut(lb + 1);
@@ -367,9 +367,11 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       mmask |= (yr != yr) ? (1u << u) : 0u;
     }
     amask = __reduce_or_sync(FULL, mmask);       // cells of the tile with at least one missing marker
-    if (!HAS_IDX && amask && p.noise_mode != CYTOF_NOISE_EXTERNAL) {
-      // consecutive rows: the tile lies in 2 (aligned) or 3 Philox blocks of 4 global rows.  Their normals go
-      // to a [12][32] staging area (row = global row - 4 grp0) and the NaNs are replaced by plain copies.
+    if (amask && p.noise_mode != CYTOF_NOISE_EXTERNAL) {
+      // The draws are keyed by the POSITION of the cell in the sample's batch (= its row for full batches; for a
+      // gathered minibatch the reference draws a dense (B_i, J) normal per step as well, vae.py:33), so the tile lies
+      // in 2 (aligned) or 3 Philox blocks of 4 positions.  Their normals go to a [12][32] staging area
+      // (row = position - 4 grp0) and the NaNs are replaced by plain copies.
       const unsigned long long grow0 = grow_base + (unsigned long long)(first_row + tn);
       const unsigned a = (unsigned)grow0 & 3u;
       const unsigned long long grp0 = grow0 >> 2;
@@ -388,27 +390,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 #pragma unroll
       for (int u = 0; u < kTile; ++u)
         if ((mmask >> u) & 1u) src[u * 32 + lane] = nzr[u * 32];
-    } else if (amask) {
-      unsigned long long grp_c = ~0ull;          // Philox block in the cache: 4 consecutive global rows
-      float nz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1      // a real loop: ONE copy of the Philox rounds in the instruction stream
-      for (int u = 0; u < kTile; ++u) {
-        if (!((amask >> u) & 1u)) continue;      // warp-uniform
-        const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
-        float e = 0.f;
-        if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
-          if (p.eps) e = __ldg(p.eps + (cb + c_lo + tn + u) * J + lane);
-        } else {
-          const unsigned long long grow = grow_base + (unsigned long long)row;
-          if ((grow >> 2) != grp_c) {            // warp-uniform
-            grp_c = grow >> 2;
-            philox_normal4(p.seed, elbo_step(p), grp_c, philox_ctr(lane, i), nz);
-          }
-          const unsigned w = (unsigned)grow & 3u;
-          e = w == 0u ? nz[0] : (w == 1u ? nz[1] : (w == 2u ? nz[2] : nz[3]));
-        }
-        if ((mmask >> u) & 1u) src[u * 32 + lane] = e;
-      }
+    } else if (amask) {      // external noise: eps[cell of the batch][marker]
+#pragma unroll
+      for (int u = 0; u < kTile; ++u)
+        if ((mmask >> u) & 1u) src[u * 32 + lane] = p.eps ? __ldg(p.eps + (cb + c_lo + tn + u) * J + lane) : 0.f;
     }
   };
 

@@ -319,12 +319,11 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
 #pragma unroll 1
       for (int u = 0; u < kXT; ++u) {
         if (!((am >> u) & 1u)) continue;
-        const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
         float e = 0.f;
         if (p.noise_mode == CYTOF_NOISE_EXTERNAL) {
           if (p.eps) e = __ldg(p.eps + (cb + c_lo + tn + u) * J + lane);
         } else {
-          const unsigned long long grow = grow_base + (unsigned long long)row;
+          const unsigned long long grow = grow_base + (unsigned long long)(first_row + tn + u);   // position in the batch
           if ((grow >> 2) != grp_c) {
             grp_c = grow >> 2;
             philox_normal4(p.seed, elbo_step(p), grp_c, philox_ctr(lane, i), nz);
@@ -339,10 +338,9 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
         if (!((am >> (kXT + ps)) & 1u)) continue;
         const int cu = ps * CPT + tcell;
         if ((tm >> ps) & 1u) {      // only lanes whose tail entry is NaN (it exists, so the cell is in range)
-          const int row = HAS_IDX ? __ldg(idx + tn + cu) : first_row + tn + cu;
           src[cu * kXJS + jt] = p.noise_mode == CYTOF_NOISE_EXTERNAL
                                     ? (p.eps ? __ldg(p.eps + (cb + c_lo + tn + cu) * J + jt) : 0.f)
-                                    : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)row, philox_ctr(jt, i));
+                                    : philox_normal(p.seed, elbo_step(p), grow_base + (unsigned long long)(first_row + tn + cu), philox_ctr(jt, i));
         }
       }
     }

@@ -218,7 +218,7 @@ elbo_fwdbwd_umma_kernel(const ElboParams p) {
   // this CTA's cells [c_lo, c_hi) of the sample; full batch: cut points at global rows that are multiples of 8
   auto cut = [&](const long long q) -> long long {
     long long x = Bi * q / nb;
-    if (!HAS_IDX && q > 0 && q < nb) x -= (long long)((grow_base + (unsigned long long)x) & 7ull);
+    if (q > 0 && q < nb) x -= (long long)((grow_base + (unsigned long long)x) & 7ull);
     return x < 0 ? 0 : x;
   };
   const long long c_lo = cut(lb), c_hi = cut(lb + 1);
@@ -368,8 +368,9 @@ elbo_fwdbwd_umma_kernel(const ElboParams p) {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 if (p.eps && ((mm >> c) & 1u)) e[c] = __ldg(p.eps + (cb + c_lo + cell0 + c) * J + lane);
-            } else if (!HAS_IDX) {
-              // consecutive rows: the 4 cells lie in one Philox block of 4 global rows (aligned) or in two
+            } else {
+              // the draws are keyed by the POSITION in the batch (= the row for full batches): the 4 cells lie in one
+              // Philox block of 4 positions (aligned) or in two
               const unsigned long long grow0 = grow_base + (unsigned long long)(first_row + cell0);
               const unsigned a = (unsigned)grow0 & 3u;
               float n8[8];
@@ -378,14 +379,6 @@ elbo_fwdbwd_umma_kernel(const ElboParams p) {
               else n8[4] = n8[5] = n8[6] = n8[7] = 0.f;
 #pragma unroll
               for (int c = 0; c < 4; ++c) e[c] = a == 0u ? n8[c] : (a == 1u ? n8[c + 1] : (a == 2u ? n8[c + 2] : n8[c + 3]));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                if (((am >> c) & 1u) && cell0 + c < ncell) {      // warp-uniform
-                  const unsigned long long grow = grow_base + (unsigned long long)__ldg(idx + cell0 + c);
-                  e[c] = philox_normal(p.seed, elbo_step(p), grow, ctr_j);
-                }
-              }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)

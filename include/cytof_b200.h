@@ -53,7 +53,8 @@ extern "C" {
 #define CYTOF_EALIGN (-5)     /* pointer not aligned as required */
 
 #define CYTOF_NOISE_EXTERNAL 0 /* eps[C,J] supplied (parity mode; only missing entries are read) */
-#define CYTOF_NOISE_PHILOX 1   /* in-kernel Philox4x32-10 keyed by (seed, step, global row, marker) */
+#define CYTOF_NOISE_PHILOX 1   /* in-kernel Philox4x32-10 keyed by (seed, step, sample, row_global[i] + position of the cell in the
+                                 * sample's batch, marker): the global row for full batches, the minibatch slot for gathered ones */
 
 /* cytof_desc.flags: the caller's promise that y contains no NaN (the reference computes
  * m = isnan(y) once in fit.py:66; a data set whose mask is all-false may say so).  Lets the

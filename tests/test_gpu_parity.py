@@ -292,6 +292,43 @@ def test_philox_mode_matches_oracle_on_emitted_noise_and_is_shard_invariant():
     check_block(tot_blk, blk, ccf.block_layout(I, J, K, L0, L1), tol=2e-5)
 
 
+@pytest.mark.parametrize('shape', [
+    dict(I=2, J=32, K=30, L0=5, L1=3, N=[900, 700], mb=[300, 333]),      # tensor-core kernel, cfg3 shapes
+    dict(I=2, J=40, K=50, L0=8, L1=8, N=[400, 300], mb=[130, 77]),       # cfg5-shape kernel (tail markers)
+    dict(I=2, J=50, K=20, L0=3, L1=4, N=[300, 200], mb=[90, 64]),        # first kernel (J > 48)
+])
+def test_philox_mode_gathered_minibatch_is_keyed_by_position(shape):
+    """In-kernel noise for a GATHERED minibatch: the draw of (cell, marker) is keyed by the cell's position in the
+    sample's batch (the reference draws a dense (B_i, J) normal per step, vae.py:33), not by its row -- so the
+    emitted draws do not depend on idx, and every kernel family reproduces the oracle on them."""
+    I, J, K, L0, L1, N, mb = (shape[k] for k in ('I', 'J', 'K', 'L0', 'L1', 'N', 'mb'))
+    y, g = _random_problem(I, J, K, L0, L1, N, 0.3, seed=61)
+    dev = _dev()
+    eng = CellEngine([torch.tensor(t, dtype=torch.float32) for t in y], dev, K, L0, L1, True, float(np.sqrt(10.0)), 0.5,
+                     g['b'], seed=77)
+    rng = np.random.default_rng(5)
+    idx_l = [rng.permutation(n)[:b] for n, b in zip(N, mb)]
+    idx = torch.tensor(np.concatenate(idx_l), dtype=torch.int32, device=dev)
+    batch = Batch(mb, idx, None, step=3)
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    blk, ll = eng.fwdbwd(batch, G, zm)
+    blk, ll = blk.cpu().numpy().astype(np.float64), ll.cpu().numpy().copy()
+    eps = eng.philox_noise(batch).cpu().numpy()
+    # position keyed: the same draws for any other choice of rows, and for the full-batch walk over the first mb rows
+    idx2 = torch.tensor(np.concatenate([rng.permutation(n)[:b] for n, b in zip(N, mb)]), dtype=torch.int32, device=dev)
+    assert np.array_equal(eng.philox_noise(Batch(mb, idx2, None, step=3)).cpu().numpy(), eps)
+    assert np.array_equal(eng.philox_noise(Batch(mb, None, None, step=3)).cpu().numpy(), eps)
+    eps_l = list(np.split(eps.astype(np.float64), np.cumsum(mb)[:-1], axis=0))
+    y_mb = [yi[ix] for yi, ix in zip(y, idx_l)]
+    fac = np.array(N, dtype=np.float64) / np.array(mb)
+    ll_ref, lqy_ref, blk_ref, y_imp_ref = ccf.cells_fwdbwd(y_mb, eps_l, g, fac, 0.5, np.sqrt(10.0), True)
+    assert abs(ll[0] - ll_ref) <= ELBO_TOL * abs(ll_ref)
+    assert abs(ll[1] - lqy_ref) <= ELBO_TOL * abs(lqy_ref)
+    check_block(blk, blk_ref, ccf.block_layout(I, J, K, L0, L1))
+    y_imp = eng.impute(batch, G).cpu().numpy()
+    assert np.allclose(y_imp, np.concatenate(y_imp_ref), rtol=2e-6, atol=2e-6)
+
+
 def test_results_are_bitwise_reproducible():
     I, J, K, L0, L1, N = 3, 32, 30, 5, 3, [3000, 2000, 1000]
     y, g = _random_problem(I, J, K, L0, L1, N, 0.2, seed=21)
