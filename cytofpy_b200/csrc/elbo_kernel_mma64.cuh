@@ -144,7 +144,14 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   const int lb = (int)blockIdx.x - p.blk_begin[i];
   const long long cb = p.cell_begin[i];
   const long long Bi = p.cell_begin[i + 1] - cb;
-  const long long c_lo = Bi * lb / nb, c_hi = Bi * (lb + 1) / nb;
+  // this CTA's cells [c_lo, c_hi) of the sample; the cut points are moved down to a global position that is a multiple
+  // of 4, so that a 4-cell tile is exactly ONE Philox block of the imputation pre-pass
+  auto cut = [&](const long long q) -> long long {
+    long long x = Bi * q / nb;
+    if (q > 0 && q < nb) x -= (long long)(((unsigned long long)p.row_global[i] + (unsigned long long)x) & 3ull);
+    return x < 0 ? 0 : x;
+  };
+  const long long c_lo = cut(lb), c_hi = cut(lb + 1);
   const long long row_base = p.row_base[i];
   const int ncj = (J + 7) >> 3, nck = (K + 7) >> 3, mtk = (K + 15) >> 4, mtj = (J + 15) >> 4;
 
@@ -269,7 +276,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   const int ncell = (int)(c_hi - c_lo);
   const int first_row = (int)c_lo;
   const int nrounds = (ncell + kXWarps * kXT - 1) / (kXWarps * kXT);      // CTA-uniform
-  const bool vec16 = !HAS_IDX && (J & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;
+  const bool vec16 = (J & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;   // rows are 16-byte aligned, gathered or not
 
   // y rows of this warp's tile of round r -> sYb[b] (row stride kXJS); rows past the range are zeros
   auto issue_tile = [&](const int r, const int b) {
