@@ -361,7 +361,10 @@ def run_ours(args, w, rank, world, local_rank):
 
     # ---- end to end through the public API with HOST buffers: every step copies the step's
     # input rows from pinned host memory to the device and reads the ELBO back
-    y_pin = torch.cat(y, 0).pin_memory()
+    y_host = torch.cat(y, 0)
+    with cy.util.on_gpu_node(local_rank) as numa_cpus:      # the pinned copy lands on the GPU's NUMA node
+        y_pin = y_host.pin_memory()
+    del y_host
     pin_clean = not bool(torch.isnan(y_pin).any())      # host-side mask check, once (fit.py:66)
     h2d = y_pin.numel() * 4 if mb is None else cells_step * 4 * J      # rows that cross PCIe per step
     e_ev = []
@@ -463,7 +466,8 @@ def run_ours(args, w, rank, world, local_rank):
                        'l2': 'flushed between timed iterations (512 MiB fill)', 'noise': 'in-kernel philox',
                        'step': 'one CUDA-graph replay (device sampler, global fwd, per-cell kernel, finalise, global bwd + Adam)'},
             'e2e': {'value': cells_step * world / (e2e_ms * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms},
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 40, 'ms_per_step': e2e_ms,
+                    'host_cpus_bound_to_gpu_node': numa_cpus},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'elbo_fwdbwd_mma_kernel (+finalize)', 'achieved': achieved,

@@ -5,3 +5,4 @@ from .cbfile import readCB, preprocess
 
 __all__ = ['simdata', 'simdata_with_missing_values', 'synth_cytof', 'inject_missing',
            'readCB', 'preprocess']
+from .hostbind import on_gpu_node, gpu_local_cpus
