@@ -216,3 +216,16 @@ def test_model_param_and_vae_pickle_as_cpu_copies():
     y = torch.tensor([[0.5, float('nan'), 1.0, -1.0]], dtype=torch.float64)
     yi, lq = v(y, torch.isnan(y), 10)
     assert yi.shape == (1, 4) and not torch.isnan(yi).any() and yi[0, 0] == 0.5
+
+
+def test_on_gpu_node_restores_the_affinity_and_never_raises():
+    """util.on_gpu_node: without NVML / a GPU it changes nothing and yields 0; with one it must hand the calling
+    thread its previous CPU mask back (the bench's CPU-baseline leg runs later in the same process)."""
+    import os
+    import cytofpy_b200 as cy
+    before = os.sched_getaffinity(0)
+    with cy.util.on_gpu_node(0) as n:
+        inside = os.sched_getaffinity(0)
+        assert n == 0 or (n == len(inside) and inside <= before)
+    assert os.sched_getaffinity(0) == before
+    assert cy.util.gpu_local_cpus(99) == set()      # no such device: empty, no exception
