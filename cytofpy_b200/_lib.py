@@ -11,6 +11,7 @@ from . import build as _build
 MAX_SAMPLES, MAX_J, MAX_K, MAX_L = 32, 64, 64, 8
 NOISE_EXTERNAL, NOISE_PHILOX = 0, 1
 FLAG_NO_MISSING = 1
+FLAG_SAMPLE_IN_KERNEL = 2
 
 
 class Desc(C.Structure):
@@ -25,6 +26,8 @@ class Desc(C.Structure):
         ('row_global', C.c_int64 * MAX_SAMPLES),
         ('fac', C.c_double * MAX_SAMPLES),
         ('step_dev', C.c_void_p),
+        ('sampler_seed', C.c_uint64), ('sampler_step', C.c_uint64),
+        ('sampler_N', C.c_int64 * MAX_SAMPLES),
     ]
 
 

@@ -54,19 +54,7 @@ __global__ void adam_step_kernel(double* __restrict__ param, const double* __res
 }
 __global__ void adam_bump_kernel(long long* step_dev) { *step_dev += 1; }
 
-// ---- keyed bijection of [0, N): balanced Feistel network + cycle walking
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
-__host__ __device__ inline unsigned long long sampler_key(unsigned long long seed, unsigned long long step, int sample) {
-  // splitmix64 of (seed, step, sample) -> Feistel key
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(sample + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return z;
-}
+// ---- sampler kernels: the keyed bijection itself is in common.cuh (the per-cell kernels evaluate it too)
 __global__ void sample_minibatch_kernel(long long N, long long m, unsigned long long key, int hbits,
                                         int32_t* __restrict__ out, unsigned long long seed,
                                         const long long* __restrict__ step_dev, int sample) {
@@ -74,20 +62,7 @@ __global__ void sample_minibatch_kernel(long long N, long long m, unsigned long 
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   if (step_dev) key = sampler_key(seed, (unsigned long long)(*step_dev + 1), sample);
-  const uint32_t hmask = (1u << hbits) - 1u;
-  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-  unsigned long long x = (unsigned long long)t;
-  do {
-    uint32_t L = (uint32_t)(x >> hbits) & hmask, R = (uint32_t)x & hmask;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r) ^ (k1 << (r & 7))) & hmask;
-      const uint32_t nl = R;
-      R = L ^ f;
-      L = nl;
-    }
-    x = ((unsigned long long)L << hbits) | R;
-  } while (x >= (unsigned long long)N);
+  const unsigned long long x = feistel_perm(key, hbits, (unsigned long long)N, (unsigned long long)t);
   out[t] = (int32_t)x;
 }
 // all I samples in ONE launch (blockIdx.y = sample): the CUDA-graph step needs a single sampler node
@@ -107,20 +82,7 @@ __global__ void sample_minibatch_multi_kernel(const MultiSample ms, unsigned lon
   if (m >= N) { o[t] = (int32_t)t; return; }
   const unsigned long long key = sampler_key(seed, step_dev ? (unsigned long long)(*step_dev + 1) : step_host, i);
   const int hbits = ms.hbits[i];
-  const uint32_t hmask = (1u << hbits) - 1u;
-  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-  unsigned long long x = (unsigned long long)t;
-  do {
-    uint32_t L = (uint32_t)(x >> hbits) & hmask, R = (uint32_t)x & hmask;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r) ^ (k1 << (r & 7))) & hmask;
-      const uint32_t nl = R;
-      R = L ^ f;
-      L = nl;
-    }
-    x = ((unsigned long long)L << hbits) | R;
-  } while (x >= (unsigned long long)N);
+  const unsigned long long x = feistel_perm(key, hbits, (unsigned long long)N, (unsigned long long)t);
   o[t] = (int32_t)x;
 }
 __global__ void iota_kernel(long long N, int32_t* __restrict__ out) {

@@ -205,6 +205,11 @@ struct ElboParams {
   long long row_global[CYTOF_MAX_SAMPLES];
   float fac[CYTOF_MAX_SAMPLES];
   int blk_begin[CYTOF_MAX_SAMPLES + 1];
+  // CYTOF_FLAG_SAMPLE_IN_KERNEL: the kernel draws the minibatch rows itself (RowSampler below); idx is null
+  int sampler_on;
+  unsigned long long sampler_seed, sampler_step;     // the step is *step_dev + 1 when step_dev is set
+  int sampler_N[CYTOF_MAX_SAMPLES];
+  unsigned char sampler_hbits[CYTOF_MAX_SAMPLES];
 };
 
 // The heavy template instantiations live in their own translation units (variants_mma.cu,
@@ -221,6 +226,63 @@ int umma_threads();
 
 __device__ __forceinline__ uint32_t elbo_step(const ElboParams& p) {
   return p.step_dev ? (uint32_t)(*p.step_dev + 1) : p.step;
+}
+
+// ---- without-replacement minibatch: keyed bijection of [0, N) (balanced Feistel network + cycle walking); position t
+// of the minibatch is row perm(t).  Replaces np.random.choice(N_i, mb, replace=False) of reference fit.py:96-102.
+// Used by the sampler kernels (abi.cu) and, with CYTOF_FLAG_SAMPLE_IN_KERNEL, evaluated by the per-cell kernels
+// themselves, so that a minibatch step needs neither a sampler launch nor an index buffer.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ inline unsigned long long sampler_key(unsigned long long seed, unsigned long long step, int sample) {
+  // splitmix64 of (seed, step, sample) -> Feistel key
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(sample + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+__host__ __device__ inline int sampler_half_bits(long long N) {
+  int bits = 1;
+  while ((1LL << bits) < N) ++bits;
+  return (bits + 1) / 2 < 1 ? 1 : (bits + 1) / 2;
+}
+__host__ __device__ __forceinline__ unsigned long long feistel_perm(unsigned long long key, int hbits, unsigned long long N,
+                                                                    unsigned long long t) {
+  const uint32_t hmask = (1u << hbits) - 1u;
+  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  unsigned long long x = t;
+  do {
+    uint32_t L = (uint32_t)(x >> hbits) & hmask, R = (uint32_t)x & hmask;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r) ^ (k1 << (r & 7))) & hmask;
+      const uint32_t nl = R;
+      R = L ^ f;
+      L = nl;
+    }
+    x = ((unsigned long long)L << hbits) | R;
+  } while (x >= N);
+  return x;
+}
+// rows of sample i's minibatch inside a per-cell kernel: pos = position in the sample's batch on this rank
+struct RowSampler {
+  unsigned long long key, N;
+  int hbits;
+  bool identity;      // the batch is the whole sample
+  __device__ __forceinline__ int row(long long pos) const {
+    return identity ? (int)pos : (int)feistel_perm(key, hbits, N, (unsigned long long)pos);
+  }
+};
+__device__ __forceinline__ RowSampler make_row_sampler(const ElboParams& p, int i) {
+  RowSampler s;
+  s.N = (unsigned long long)p.sampler_N[i];
+  s.hbits = p.sampler_hbits[i];
+  s.identity = (unsigned long long)(p.cell_begin[i + 1] - p.cell_begin[i]) >= s.N;
+  s.key = sampler_key(p.sampler_seed, p.step_dev ? (unsigned long long)(*p.step_dev + 1) : p.sampler_step, i);
+  return s;
 }
 
 // ---- programmatic dependent launch (sm_90+): every kernel of the step is launched with the

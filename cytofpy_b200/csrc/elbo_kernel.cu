@@ -150,8 +150,10 @@ elbo_fwdbwd_kernel(const ElboParams p) {
 
   // ---------------- stream the cells of this CTA ----------------
   const int32_t* __restrict__ idx = p.idx;
+  RowSampler rsm;      // CYTOF_FLAG_SAMPLE_IN_KERNEL: rows from the sampler's keyed bijection instead of idx
+  if (p.sampler_on) rsm = make_row_sampler(p, i);
   auto row_of = [&](long long c) -> long long {
-    return row_base + (idx ? (long long)__ldg(idx + cb + c) : c);
+    return row_base + (p.sampler_on ? (long long)rsm.row(c) : (idx ? (long long)__ldg(idx + cb + c) : c));
   };
   long long c = c_lo + warp;
   long long row_cur = 0, row_next = 0;
@@ -883,6 +885,10 @@ int validate_desc(const cytof_desc* d) {
   for (int i = 0; i < d->I; ++i)
     if (d->cell_begin[i + 1] < d->cell_begin[i]) return CYTOF_EINVAL;
   if (d->noise_mode != CYTOF_NOISE_EXTERNAL && d->noise_mode != CYTOF_NOISE_PHILOX) return CYTOF_EINVAL;
+  if (d->flags & CYTOF_FLAG_SAMPLE_IN_KERNEL) {     // the minibatch of every sample must fit its sampling domain
+    for (int i = 0; i < d->I; ++i)
+      if (d->sampler_N[i] < d->cell_begin[i + 1] - d->cell_begin[i] || d->sampler_N[i] > 0x7fffffffLL) return CYTOF_EINVAL;
+  }
   if (!pick_variant(d->J, d->K, d->L0, d->L1)) return CYTOF_ESHAPE;
   return CYTOF_OK;
 }
@@ -901,6 +907,15 @@ void fill_params(const cytof_desc* d, ElboParams* p) {
     p->row_base[i] = d->row_base[i];
     p->row_global[i] = d->row_global[i];
     p->fac[i] = (float)d->fac[i];
+  }
+  p->sampler_on = (d->flags & CYTOF_FLAG_SAMPLE_IN_KERNEL) ? 1 : 0;
+  p->sampler_seed = d->sampler_seed;
+  if (p->sampler_on) {
+    p->sampler_step = d->sampler_step;
+    for (int i = 0; i < d->I; ++i) {
+      p->sampler_N[i] = (int)d->sampler_N[i];
+      p->sampler_hbits[i] = (unsigned char)sampler_half_bits(d->sampler_N[i]);
+    }
   }
 }
 
@@ -955,6 +970,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
                   const float* globals, const uint64_t* zmask, float* grad_block, double* ll_lqy,
                   double* packed, void* workspace, size_t workspace_bytes_, cudaStream_t stream,
                   cudaError_t* err, const cytof_peer_desc* peer) {
+  if ((d->flags & CYTOF_FLAG_SAMPLE_IN_KERNEL) && idx) return CYTOF_EINVAL;     // one source of rows, not two
   const Variant* v64 = pick_variant64(d);
   const Variant* vu = v64 ? nullptr : pick_variant_umma(d, y);
   const Variant* v = v64 ? v64 : (vu ? vu : pick_variant(d->J, d->K, d->L0, d->L1));
@@ -966,8 +982,9 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15;
   p.partials = reinterpret_cast<float*>(wp);
   const size_t smem = fused_smem_bytes(v, d->J, d->K, d->L0, d->L1);
-  const int fi = v64 ? (d->model_noisy ? 1 : 0) + (idx ? 2 : 0) + (d->J - 32 > 8 ? 4 : 0)
-                     : (d->model_noisy ? 1 : 0) + (idx ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
+  const bool gathered = idx != nullptr || (d->flags & CYTOF_FLAG_SAMPLE_IN_KERNEL);
+  const int fi = v64 ? (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + (d->J - 32 > 8 ? 4 : 0)
+                     : (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
   const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem));
   const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
   const size_t need = sizeof(float) * (size_t)pl.total * (size_t)nblocks + (wp - reinterpret_cast<uintptr_t>(workspace));

@@ -230,14 +230,25 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 
   // y rows of the tile starting at cell tn -> sYb[b]; rows past the end of the range and lanes
   // >= J are zero-filled, so the arithmetic below needs no validity selects
+  // gathered batches: lane l fetches the row of cell (l & 7) of the tile -- from idx, or (CYTOF_FLAG_SAMPLE_IN_KERNEL)
+  // by evaluating the sampler's keyed bijection at the cell's position -- and the lanes exchange them by shuffle
+  RowSampler rsm;
+  if (HAS_IDX && p.sampler_on) rsm = make_row_sampler(p, i);
+  auto tile_rows = [&](const int tn) -> int {
+    const int u8 = lane & 7;
+    if (!HAS_IDX || tn + u8 >= ncell) return 0;
+    return p.sampler_on ? rsm.row(c_lo + tn + u8) : __ldg(idx + tn + u8);
+  };
   auto issue_tile = [&](const int tn, const int b) {
     float* dst = sYb + b * (kTile * 32);
+    const int row8 = tile_rows(tn);
     if (vec16) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = lane + 32 * h, u = c >> 3, part = c & 7;
+        const int rowg = HAS_IDX ? __shfl_sync(FULL, row8, u) : 0;
         if (tn + u < ncell) {
-          const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+          const int row = HAS_IDX ? rowg : first_row + tn + u;
           cp_async16(dst + u * 32 + 4 * part, ysamp + (size_t)row * 32 + 4 * part);
         } else {
           *reinterpret_cast<float4*>(dst + u * 32 + 4 * part) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,8 +257,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     } else {
 #pragma unroll
       for (int u = 0; u < kTile; ++u) {
+        const int rowg = HAS_IDX ? __shfl_sync(FULL, row8, u) : 0;
         if (ok && tn + u < ncell) {
-          const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+          const int row = HAS_IDX ? rowg : first_row + tn + u;
           cp_async4(dst + u * 32 + lane, ysamp + (size_t)row * J + lane);
         } else {
           dst[u * 32 + lane] = 0.f;

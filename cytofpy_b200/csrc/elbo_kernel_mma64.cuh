@@ -279,13 +279,19 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   const bool vec16 = (J & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;   // rows are 16-byte aligned, gathered or not
 
   // y rows of this warp's tile of round r -> sYb[b] (row stride kXJS); rows past the range are zeros
+  RowSampler rsm;      // CYTOF_FLAG_SAMPLE_IN_KERNEL: the rows come from the sampler's keyed bijection, not from idx
+  if (HAS_IDX && p.sampler_on) rsm = make_row_sampler(p, i);
   auto issue_tile = [&](const int r, const int b) {
     const int tn = (r * kXWarps + warp) * kXT;
     float* dst = sYb + b * (kXT * kXJS);
+    int row4 = 0;      // lane l: row of cell (l & 3) of the tile
+    if (HAS_IDX && tn + (lane & 3) < ncell)
+      row4 = p.sampler_on ? rsm.row(c_lo + tn + (lane & 3)) : __ldg(idx + tn + (lane & 3));
 #pragma unroll
     for (int u = 0; u < kXT; ++u) {
+      const int rowg = HAS_IDX ? __shfl_sync(FULL, row4, u) : 0;
       if (tn + u < ncell) {
-        const int row = HAS_IDX ? __ldg(idx + tn + u) : first_row + tn + u;
+        const int row = HAS_IDX ? rowg : first_row + tn + u;
         const float* src = ysamp + (size_t)row * J;
         if (vec16) {
           if (4 * lane < J) cp_async16(dst + u * kXJS + 4 * lane, src + 4 * lane);

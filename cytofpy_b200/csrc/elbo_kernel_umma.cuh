@@ -722,6 +722,8 @@ elbo_fwdbwd_umma_kernel(const ElboParams p) {
       const int32_t* __restrict__ idx = p.idx + (HAS_IDX ? (cb + c_lo) : 0);
       const float* __restrict__ ysamp = p.y + (size_t)row_base * J;
       const bool whole = !HAS_IDX && J == 32;          // a quarter is one contiguous 4 KB block of the matrix
+      RowSampler rsm;                                  // CYTOF_FLAG_SAMPLE_IN_KERNEL
+      if (HAS_IDX && p.sampler_on) rsm = make_row_sampler(p, i);
       const uint32_t rowbytes = 4u * (uint32_t)J;
       for (int Q = 0; Q < NQ && good; ++Q) {
         const int slot = Q & 7;
@@ -738,7 +740,8 @@ elbo_fwdbwd_umma_kernel(const ElboParams p) {
         if (whole) {
           if (lane == 0) bulk_g2s(dst, ysamp + (size_t)((int)c_lo + 32 * Q) * 32, (uint32_t)nrows * 128u, bar(kBYFull + slot));
         } else if (lane < nrows) {
-          const int row = HAS_IDX ? __ldg(idx + 32 * Q + lane) : (int)c_lo + 32 * Q + lane;
+          const int row = !HAS_IDX ? (int)c_lo + 32 * Q + lane
+                                   : (p.sampler_on ? rsm.row(c_lo + 32 * Q + lane) : __ldg(idx + 32 * Q + lane));
           bulk_g2s(dst + 128u * lane, ysamp + (size_t)row * J, rowbytes, bar(kBYFull + slot));
         }
       }

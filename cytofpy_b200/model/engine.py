@@ -19,10 +19,16 @@ def _ptr(t):
 class Batch:
     """The cells of one step: per-sample counts, (optional) gathered row indices
     on the device and (optional) external noise."""
-    __slots__ = ('counts', 'idx', 'eps', 'step')
+    __slots__ = ('counts', 'idx', 'eps', 'step', 'sampler')
 
-    def __init__(self, counts, idx=None, eps=None, step=0):
+    def __init__(self, counts, idx=None, eps=None, step=0, sampler=None):
+        """`sampler` = (seed, step): the per-cell kernel draws the minibatch rows itself
+        (CYTOF_FLAG_SAMPLE_IN_KERNEL) -- the rows cytof_sample_minibatch would write for that seed and step;
+        `idx` must then be None."""
         self.counts, self.idx, self.eps, self.step = [int(c) for c in counts], idx, eps, int(step)
+        self.sampler = sampler
+        if sampler is not None and idx is not None:
+            raise ValueError('Batch: either explicit row indices or the in-kernel sampler, not both')
 
     @property
     def ncells(self):
@@ -78,6 +84,11 @@ class CellEngine:
         d.noise_mode = noise_mode
         d.noisy_sd, d.scale = self.noisy_sd, self.scale
         d.flags = _lib.FLAG_NO_MISSING if self.no_missing else 0
+        if batch.sampler is not None:
+            d.flags |= _lib.FLAG_SAMPLE_IN_KERNEL
+            d.sampler_seed, d.sampler_step = int(batch.sampler[0]) & (2 ** 64 - 1), int(batch.sampler[1])
+            for i in range(self.I):
+                d.sampler_N[i] = int(self.N_local[i])
         d.seed, d.step = self.seed & (2 ** 64 - 1), batch.step
         d.step_dev = self.step_dev
         cb = 0

@@ -202,8 +202,13 @@ class FusedStep:
             from .train import device_minibatch
             self.step([range(n) for n in eng.N_local] if full else
                       device_minibatch(m, minibatch_size, 0, self.g.seed))
-        idx_buf = None if full else torch.empty(sum(counts), dtype=torch.int32, device=self.dev)
-        batch = Batch(counts, idx_buf, None, step=0)
+        # minibatches: the per-cell kernel evaluates the sampler's keyed bijection itself (CYTOF_FLAG_SAMPLE_IN_KERNEL,
+        # step read from step_dev): no sampler node and no index buffer in the graph.  CYTOF_SAMPLER_KERNEL=1 keeps the
+        # separate sampler launch (A/B; the rows are the same)
+        import os
+        in_kernel = not full and os.environ.get('CYTOF_SAMPLER_KERNEL', '0') != '1'
+        idx_buf = None if (full or in_kernel) else torch.empty(sum(counts), dtype=torch.int32, device=self.dev)
+        batch = Batch(counts, idx_buf, None, step=0, sampler=(self.g.seed, 0) if in_kernel else None)
         cg = m._counts_global(batch)                     # (cached) collective outside the capture
         self.step_dev.fill_(self.t)
         sd = self.step_dev.data_ptr()

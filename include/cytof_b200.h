@@ -60,10 +60,16 @@ extern "C" {
  * m = isnan(y) once in fit.py:66; a data set whose mask is all-false may say so).  Lets the
  * library pick kernels without the imputation path; a NaN in y then yields a NaN ELBO. */
 #define CYTOF_FLAG_NO_MISSING 1
+/* cytof_desc.flags: the per-cell kernel draws the minibatch rows ITSELF (idx must be NULL): cell c of sample i reads the
+ * row cytof_sample_minibatch* would have written to idx[c] for (sampler_seed, step, sample i, N = sampler_N[i],
+ * m = cell_begin[i+1] - cell_begin[i]); step = *step_dev + 1 when step_dev is set, else sampler_step.  A minibatch step
+ * then needs neither a sampler launch nor an index buffer (reference fit.py:96-102 is a host permutation per step). */
+#define CYTOF_FLAG_SAMPLE_IN_KERNEL 2
 
 /* One ELBO evaluation ("step") over C = sum_i B_i cells.
  * The step's cell list is sample-major: cells [cell_begin[i], cell_begin[i+1]) belong to sample i.
- * Cell c of sample i reads row  row_base[i] + (idx ? idx[c] : c - cell_begin[i])  of y. */
+ * Cell c of sample i reads row  row_base[i] + (idx ? idx[c] : c - cell_begin[i])  of y
+ * (CYTOF_FLAG_SAMPLE_IN_KERNEL: row_base[i] + perm_i(c - cell_begin[i]), see the flag). */
 typedef struct cytof_desc {
   int32_t I, J, K, L0, L1;
   int32_t model_noisy; /* Model.py:259-266 on/off */
@@ -81,6 +87,10 @@ typedef struct cytof_desc {
    * read on the device, and `step` is ignored.  cytof_global_bwd_adam_f64 bumps the counter at
    * the end of a step, so one captured graph advances the noise / sampler / Adam step by itself. */
   const int64_t* step_dev;
+  /* CYTOF_FLAG_SAMPLE_IN_KERNEL only (ignored otherwise) */
+  uint64_t sampler_seed;
+  uint64_t sampler_step;
+  int64_t sampler_N[CYTOF_MAX_SAMPLES]; /* rows of sample i the minibatch is drawn from (this rank's shard) */
 } cytof_desc;
 
 /* `globals` (float, device): the transformed global sample of this step, packed as

@@ -34,7 +34,9 @@ def test_desc_struct_matches_header():
     hdr = open(os.path.join(ROOT, 'include', 'cytof_b200.h')).read()
     assert int(re.search(r'#define CYTOF_MAX_SAMPLES (\d+)', hdr).group(1)) == _lib.MAX_SAMPLES
     # 8 int32 + 2 float + 2 uint64 + 33 int64 + 32 int64 + 32 int64 + 32 double + 1 pointer
-    assert C.sizeof(_lib.Desc) == 8 * 4 + 2 * 4 + 2 * 8 + 33 * 8 + 3 * 32 * 8 + 8
+    # + the in-kernel sampler's 2 uint64 + 32 int64
+    assert C.sizeof(_lib.Desc) == 8 * 4 + 2 * 4 + 2 * 8 + 33 * 8 + 3 * 32 * 8 + 8 + 2 * 8 + 32 * 8
+    assert _lib.Desc.sampler_seed.offset == _lib.Desc.step_dev.offset + 8
     # cytof_peer_desc: 2 int32 + uint64 + 16 pointers + 1 pointer
     assert C.sizeof(_lib.PeerDesc) == 2 * 4 + 8 + 16 * 8 + 8
     assert _lib.Desc.cell_begin.offset == 56

@@ -329,6 +329,49 @@ def test_philox_mode_gathered_minibatch_is_keyed_by_position(shape):
     assert np.allclose(y_imp, np.concatenate(y_imp_ref), rtol=2e-6, atol=2e-6)
 
 
+@pytest.mark.parametrize('shape', [
+    dict(I=3, J=32, K=30, L0=5, L1=3, N=[4000, 2500, 300], mb=[500, 500, 300]),     # tensor-core kernel; last sample whole
+    dict(I=2, J=40, K=50, L0=8, L1=8, N=[900, 700], mb=[130, 77]),                   # cfg5-shape kernel
+    dict(I=2, J=50, K=20, L0=3, L1=4, N=[300, 200], mb=[90, 64]),                    # first kernel (J > 48)
+    dict(I=2, J=20, K=12, L0=3, L1=3, N=[1000, 513], mb=[64, 512]),                  # rows narrower than 128 bytes
+])
+@pytest.mark.parametrize('nan_rate', [0.0, 0.25])
+def test_in_kernel_minibatch_sampler_equals_the_sampler_kernel(shape, nan_rate):
+    """CYTOF_FLAG_SAMPLE_IN_KERNEL: the per-cell kernel evaluates the sampler's keyed bijection at each cell's position
+    instead of reading idx.  Bitwise the same gradient block and ll as the same launch fed with the rows
+    cytof_sample_minibatch writes for that (seed, step, sample) -- for every kernel family."""
+    I, J, K, L0, L1, N, mb = (shape[k] for k in ('I', 'J', 'K', 'L0', 'L1', 'N', 'mb'))
+    y, g = _random_problem(I, J, K, L0, L1, N, nan_rate, seed=71)
+    dev = _dev()
+    eng = CellEngine([torch.tensor(t, dtype=torch.float32) for t in y], dev, K, L0, L1, True, float(np.sqrt(10.0)), 1.0,
+                     g['b'], seed=5)
+    G, zm = pack_globals(g, I, True).to(dev), pack_zmask(g['Z']).to(dev)
+    lib = eng.lib
+    import ctypes as C
+    sseed, sstep = 991, 12
+    parts = []
+    for i, (n, m) in enumerate(zip(N, mb)):
+        t = torch.empty(m, dtype=torch.int32, device=dev)
+        rc = lib.cytof_sample_minibatch(n, m, sseed, sstep, i, C.c_void_p(t.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        assert rc == 0
+        parts.append(t)
+    idx = torch.cat(parts)
+    for n, m, t in zip(N, mb, parts):          # a without-replacement draw (or the whole sample)
+        v = t.cpu().numpy()
+        assert len(set(v.tolist())) == m and v.min() >= 0 and v.max() < n
+    blk_a, ll_a = eng.fwdbwd(Batch(mb, idx, None, step=4), G, zm)
+    blk_a, ll_a = blk_a.clone(), ll_a.clone()
+    blk_b, ll_b = eng.fwdbwd(Batch(mb, None, None, step=4, sampler=(sseed, sstep)), G, zm)
+    assert torch.equal(blk_a, blk_b) and torch.equal(ll_a, ll_b)
+    assert torch.isfinite(blk_b).all() and torch.isfinite(ll_b).all()
+    # a different sampler step draws different rows
+    blk_c, ll_c = eng.fwdbwd(Batch(mb, None, None, step=4, sampler=(sseed, sstep + 1)), G, zm)
+    assert not torch.equal(ll_a, ll_c)     # (ll, not the block: at rho == 0 the block does not depend on the rows)
+    with pytest.raises(ValueError):
+        Batch(mb, idx, None, step=4, sampler=(sseed, sstep))
+
+
 def test_results_are_bitwise_reproducible():
     I, J, K, L0, L1, N = 3, 32, 30, 5, 3, [3000, 2000, 1000]
     y, g = _random_problem(I, J, K, L0, L1, N, 0.2, seed=21)

@@ -334,3 +334,28 @@ def test_multi_sample_sampler_equals_per_sample_calls():
     torch.cuda.synchronize()
     assert torch.equal(out2, ref)
     assert torch.equal(out[-500:].cpu(), torch.arange(500, dtype=torch.int32))
+
+
+def test_graph_step_with_in_kernel_sampler_equals_the_sampler_kernel(monkeypatch):
+    """capture() for minibatches lets the per-cell kernel draw the rows (no sampler node, no index buffer);
+    CYTOF_SAMPLER_KERNEL=1 keeps the separate sampler launch.  Same rows, so the same parameters bit for bit."""
+    from cytofpy_b200.model.fused import FusedStep
+    thetas, launches = [], []
+    for env in ('0', '1'):
+        monkeypatch.setenv('CYTOF_SAMPLER_KERNEL', env)
+        torch.manual_seed(3)
+        s = cy.util.synth_cytof([3000, 2000, 2500], 32, [100.] * 5, 5, 3, seed=6)
+        y = [torch.from_numpy(a) for a in s['y']]
+        priors = cy.model.default_priors([t.double() for t in y], K=30, L=[5, 3], y_bounds=[-5., -3.5, -2.])
+        model = cy.model.Model(y=y, priors=priors, verbose=-1, device=torch.device('cuda', 0), noise='philox', seed=1)
+        fs = FusedStep(model, lr=1e-2, seed=1)
+        fs.capture(400)
+        for _ in range(6):
+            sc = fs.graph_step()
+        torch.cuda.synchronize()
+        assert torch.isfinite(sc).all()
+        thetas.append(fs.theta.clone())
+        launches.append(fs._graph_launches)
+        fs.release_graph()
+    assert torch.equal(thetas[0], thetas[1])
+    assert launches[0] == launches[1] - 1

@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--mb', type=int, default=0)
     ap.add_argument('--n', type=int, default=0, help='cells per sample (overrides the workload)')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--sampler', action='store_true', help='with --mb: the kernel draws the rows itself (no idx)')
     ap.add_argument('--force-missing', action='store_true', help='kernels with the imputation path even for clean data')
     a = ap.parse_args()
     I, n, J, K, L0, L1 = SH[a.workload]
@@ -55,7 +56,7 @@ def main():
     eng.row_base = np.arange(I + 1, dtype=np.int64) * n
     if a.mb:
         idx = torch.cat([torch.randperm(n, device=dev, generator=g)[:a.mb].to(torch.int32) for _ in range(I)])
-        batch = Batch([a.mb] * I, idx, None, step=1)
+        batch = Batch([a.mb] * I, None, None, step=1, sampler=(7, 3)) if a.sampler else Batch([a.mb] * I, idx, None, step=1)
     else:
         batch = Batch([n] * I, None, None, step=1)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
