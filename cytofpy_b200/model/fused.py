@@ -63,6 +63,7 @@ def recognise_priors(priors, model_noisy):
 
 
 class FusedStep:
+    IN_KERNEL_SAMPLER_MAX_CELLS = 32768     # see capture()
     def __init__(self, model, lr=1e-1, betas=(0.9, 0.999), adam_eps=1e-8, seed=0, allreduce='peer'):
         hyp = recognise_priors(model.priors, model.model_noisy)
         if hyp is None:
@@ -202,11 +203,15 @@ class FusedStep:
             from .train import device_minibatch
             self.step([range(n) for n in eng.N_local] if full else
                       device_minibatch(m, minibatch_size, 0, self.g.seed))
-        # minibatches: the per-cell kernel evaluates the sampler's keyed bijection itself (CYTOF_FLAG_SAMPLE_IN_KERNEL,
-        # step read from step_dev): no sampler node and no index buffer in the graph.  CYTOF_SAMPLER_KERNEL=1 keeps the
-        # separate sampler launch (A/B; the rows are the same)
+        # small minibatches: the per-cell kernel evaluates the sampler's keyed bijection itself
+        # (CYTOF_FLAG_SAMPLE_IN_KERNEL, step read from step_dev): no sampler node and no index buffer in the graph
+        # (cfg2: 55.2 -> 53.2 us per step).  The cycle-walking bijection diverges inside a warp, so for LARGE gathered
+        # batches the separate, fully parallel sampler kernel wins (8 x 100 k cells: kernel 0.269 ms with idx, 0.310 ms
+        # sampling in the kernel); the crossover is ~40 k cells.  CYTOF_SAMPLER_KERNEL=1 forces the sampler launch (A/B;
+        # the rows are the same either way)
         import os
-        in_kernel = not full and os.environ.get('CYTOF_SAMPLER_KERNEL', '0') != '1'
+        in_kernel = (not full and sum(counts) <= self.IN_KERNEL_SAMPLER_MAX_CELLS
+                     and os.environ.get('CYTOF_SAMPLER_KERNEL', '0') != '1')
         idx_buf = None if (full or in_kernel) else torch.empty(sum(counts), dtype=torch.int32, device=self.dev)
         batch = Batch(counts, idx_buf, None, step=0, sampler=(self.g.seed, 0) if in_kernel else None)
         cg = m._counts_global(batch)                     # (cached) collective outside the capture
