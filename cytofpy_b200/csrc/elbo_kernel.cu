@@ -791,7 +791,7 @@ static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5, 0, 0), CYTOF_VA
                                        CYTOF_VARIANT_MMA64(5, 5, 0, 1), CYTOF_VARIANT_MMA64(8, 8, 1, 1) };
 static const Variant* pick_variant64(const cytof_desc* d) {
   if (!CYTOF_MMA64) return nullptr;
-  if (d->J <= 32 || d->J > 48 || d->K > 64) return nullptr;
+  if (d->J > 48 || d->K > 64 || (d->J <= 32 && d->K <= 32)) return nullptr;     // J, K <= 32: the 8-cell-tile kernel
   const int first = (d->flags & CYTOF_FLAG_NO_MISSING) ? 0 : 2;
   for (int q = first; q < first + 2; ++q)
     if (kVariants64[q].lm0 >= d->L0 && kVariants64[q].lm1 >= d->L1) return &kVariants64[q];

@@ -1,5 +1,6 @@
 // Tensor-core fused ELBO kernel for 32 < J <= 48 markers, K <= 64 features, L <= 8 components
-// (BASELINE cfg5: J = 40, K = 50, L = 8/8).  MISSING = false compiles the imputation path out.
+// (BASELINE cfg5: J = 40, K = 50, L = 8/8), and for J <= 32 markers with 32 < K <= 64 features (main lanes >= J are
+// masked, the tail pass runs empty).  MISSING = false compiles the imputation path out.
 //
 // The first SIMT kernel needs 1,767 warp-instructions per cell at these shapes (bit-mask Z gating,
 // two markers per lane, register spills; profiles/README.md).  This kernel keeps the structure of
@@ -173,6 +174,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     (second ? sZ : sZT)[mc * 32 + ln] = make_uint4(v[0], v[1], v[2], v[3]);
   }
   for (int e = lane; e < 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS; e += 32) wbase[e] = 0.f;   // D, g, A0, y^2 tiles
+  for (int e = lane; e < 2 * kXT * kXJS; e += 32) sYb[e] = 0.f;       // y buffers: columns >= J are never written by the copies
 #if CYTOF_X_TMEM
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_base_s)) : "memory");
@@ -193,6 +195,10 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   const float nh2 = -0.5f * inv_sig2 * kLog2e;
   const float cbase = (-logf(sig) - kHalfLog2Pi) * kLog2e;
   const float fac = p.fac[i];
+  // main lanes: marker `lane`, live if lane < J (always when J > 32)
+  const bool okm = lane < J;
+  const float okmf = okm ? 1.f : 0.f;
+  const int jm = okm ? lane : 0;
   // tail lane -> (cell within the pass, tail marker)
   const int tcell = lane / TP, jt = 32 + lane % TP;
   const bool tail_ok = jt < J;
@@ -216,7 +222,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       b[x] = live ? -2.f * nh2 * m[x] : 0.f;
       const float base = fmaf(nh2 * m[x], m[x], cbase);
       const float* le = G + (z1 ? gl.le1 : gl.le0);
-      am[x] = live ? fmaf(le[(i * J + lane) * Lz + ll], kLog2e, base) : kNegBig;
+      am[x] = (okm && live) ? fmaf(le[(i * J + jm) * Lz + ll], kLog2e, base) : ((okm || l != 0) ? kNegBig : 0.f);
       at[x] = (tail_ok && live) ? fmaf(le[(i * J + jtt) * Lz + ll], kLog2e, base) : (l == 0 ? 0.f : kNegBig);
     }
 #pragma unroll
@@ -236,7 +242,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   }
   // imputation parameters of this lane's main marker and tail marker (vae.py:12-13), missingness b
   const int jtl = tail_ok ? jt : 0;
-  const float vm_m = G[gl.vm + i * J + lane], vls_m = G[gl.vls + i * J + lane], sd_m = expf(vls_m);
+  const float vm_m = G[gl.vm + i * J + jm], vls_m = G[gl.vls + i * J + jm], sd_m = expf(vls_m);
   const float vm_t = G[gl.vm + i * J + jtl], vls_t = G[gl.vls + i * J + jtl], sd_t = expf(vls_t);
   const float b0 = G[gl.b + 3 * i], b1 = G[gl.b + 3 * i + 1], b2 = G[gl.b + 3 * i + 2];
   const unsigned long long grow_base = (unsigned long long)p.row_global[i];
@@ -296,7 +302,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
         if (vec16) {
           if (4 * lane < J) cp_async16(dst + u * kXJS + 4 * lane, src + 4 * lane);
         } else {
-          cp_async4(dst + u * kXJS + lane, src + lane);
+          if (lane < J) cp_async4(dst + u * kXJS + lane, src + lane);
           if (32 + lane < J) cp_async4(dst + u * kXJS + 32 + lane, src + 32 + lane);
         }
       } else {
@@ -389,10 +395,10 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     sR[un * 32 + lane] = make_float2(rr * st.S1, rr * st.S0);
     uint32_t dh, dl;
     if (un < kXT) {
-      split_tf32(A1 - A0, dh, dl);
+      split_tf32(okmf * (A1 - A0), dh, dl);
       sD[(2 * un) * kXDS + lane] = __uint_as_float(dh);
       sD[(2 * un + 1) * kXDS + lane] = __uint_as_float(dl);
-      sA[un * kXDS + lane] = A0;
+      sA[un * kXDS + lane] = okmf * A0;
       if (NOISY) sY[un * kXDS + lane] = st.yv * st.yv;
 #if CYTOF_X_TMEM
       udh[un] = __uint_as_float(dh);
@@ -422,7 +428,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   auto phase_b = [&](const int un, const float* src, const unsigned mm, const unsigned tm, const unsigned am) {
     if (un < kXT) {
       const float c1 = sA[un * kXDS + lane];
-      const float c0 = sS[un] - c1;
+      const float c0 = okmf * sS[un] - c1;
       const float x = src[un * kXJS + lane];
       const float yv = (MISSING && ((mm >> un) & 1u)) ? fmaf(sd_m, x, vm_m) : x;
       const float wd = mix_backward<LM0, NPT, MISSING>(yv, mc0, mc1, c0, c1, sR[un * 32 + lane], ee[un], mup, swm, swym, sq);
@@ -792,14 +798,16 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     const int l = z1 ? x - LM0 : x;
     if (l < (z1 ? L1 : L0)) {
       const int base = (z1 ? pl.sw1 : pl.sw0) + l * J;
-      mine[base + lane] = vm_;
+      if (okm) mine[base + lane] = vm_;
       if (lane < TP && tail_ok) mine[base + jt] = swt_f[x];
     }
   }
-  if (MISSING) {
+  if (MISSING && okm) {
     mine[pl.dvm + lane] = dvm_m;
     mine[pl.dvls + lane] = dvls_m;
     mine[pl.nm + lane] = nm_m;
+  }
+  if (MISSING) {
     if (lane < TP && tail_ok) {
       mine[pl.dvm + jt] = dvm_t;
       mine[pl.dvls + jt] = dvls_t;

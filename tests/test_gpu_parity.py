@@ -148,6 +148,9 @@ def _random_problem(I, J, K, L0, L1, N, nan_rate, seed, model_noisy=True):
     dict(I=2, J=33, K=30, L0=3, L1=3, N=[64, 65]),       # J just over one warp
     dict(I=2, J=64, K=64, L0=8, L1=8, N=[40, 24]),       # compiled maxima
     dict(I=32, J=8, K=4, L0=3, L1=3, N=[5] * 32),        # max number of samples
+    dict(I=2, J=20, K=40, L0=3, L1=3, N=[70, 33]),       # J <= 32 with K > 32: the cfg5-shape kernel, main lanes masked
+    dict(I=2, J=32, K=64, L0=5, L1=5, N=[64, 65]),
+    dict(I=1, J=5, K=33, L0=8, L1=2, N=[50]),
 ])
 @pytest.mark.parametrize('noisy', [True, False])
 def test_kernel_random_shapes(shape, noisy):
@@ -173,11 +176,13 @@ def test_kernel_random_shapes(shape, noisy):
     dict(I=3, J=45, K=64, L0=5, L1=3, N=[64, 130, 33]),  # two tail passes of 2 cells x 16 markers, K at the maximum
     dict(I=1, J=33, K=9, L0=2, L1=2, N=[301]),           # one tail marker, few features
     dict(I=2, J=48, K=33, L0=8, L1=5, N=[97, 40]),       # J at the kernel's maximum
+    dict(I=2, J=30, K=50, L0=5, L1=5, N=[150, 77]),      # J <= 32 with K > 32 (16-byte rows: no, 120 B), masked main lanes
+    dict(I=2, J=28, K=36, L0=3, L1=5, N=[90, 41]),       # the same with 16-byte aligned rows
 ])
 @pytest.mark.parametrize('noisy', [True, False])
 @pytest.mark.parametrize('gather', [True, False])
 def test_kernel_wide_shapes_without_missing(shape, noisy, gather):
-    """32 < J <= 48 without NaN: the tensor-core kernel with packed tail markers and CTA-cooperative
+    """32 < J <= 48 (and J <= 32 with K > 32) without NaN: the tensor-core kernel with packed tail markers and CTA-cooperative
     dZ (elbo_kernel_mma64.cuh) against the closed-form oracle; ragged tiles, gathered and in-order rows."""
     I, J, K, L0, L1, N = (shape[k] for k in ('I', 'J', 'K', 'L0', 'L1', 'N'))
     y, g = _random_problem(I, J, K, L0, L1, N, 0.0, seed=I * 1000 + J)
