@@ -789,9 +789,17 @@ static const Variant kVariants[] = {
 // [0..1]: kernels without the imputation path (CYTOF_FLAG_NO_MISSING), [2..3]: with it
 static const Variant kVariants64[] = { CYTOF_VARIANT_MMA64(5, 5, 0, 0), CYTOF_VARIANT_MMA64(8, 8, 1, 0),
                                        CYTOF_VARIANT_MMA64(5, 5, 0, 1), CYTOF_VARIANT_MMA64(8, 8, 1, 1) };
+// 48 < J <= 64 with L0, L1 <= 5: the WIDE layout of the same kernel (NTP = 4); [0] without, [1] with the imputation path
+#define CYTOF_VARIANT_MMA64W(a, b, lidx, miss) \
+  { a, b, 2, 2, kXWarpFloatsW, kXZFloatsW, CYTOF_FN8(mma64_kernel_fn, lidx, miss), true, kXThreads }
+static const Variant kVariants64W[] = { CYTOF_VARIANT_MMA64W(5, 5, 2, 0), CYTOF_VARIANT_MMA64W(5, 5, 2, 1) };
 static const Variant* pick_variant64(const cytof_desc* d) {
   if (!CYTOF_MMA64) return nullptr;
-  if (d->J > 48 || d->K > 64 || (d->J <= 32 && d->K <= 32)) return nullptr;     // J, K <= 32: the 8-cell-tile kernel
+  if (d->K > 64 || d->J > 64 || (d->J <= 32 && d->K <= 32)) return nullptr;     // J, K <= 32: the 8-cell-tile kernel
+  if (d->J > 48) {      // WIDE layout; L = 8/8 at these widths does not fit the register file (-> first kernel)
+    const Variant* w = &kVariants64W[(d->flags & CYTOF_FLAG_NO_MISSING) ? 0 : 1];
+    return (w->lm0 >= d->L0 && w->lm1 >= d->L1) ? w : nullptr;
+  }
   const int first = (d->flags & CYTOF_FLAG_NO_MISSING) ? 0 : 2;
   for (int q = first; q < first + 2; ++q)
     if (kVariants64[q].lm0 >= d->L0 && kVariants64[q].lm1 >= d->L1) return &kVariants64[q];
@@ -855,13 +863,15 @@ int max_grid_blocks() { return device_sm_count() * kMaxCtasPerSm + CYTOF_MAX_SAM
 // resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached per
 // device; re-evaluated when a different problem shape changes the shared-memory footprint)
 struct OccEntry { size_t smem, smem_attr; int occ; };
-static OccEntry g_occ[64][24][8] = {};
+static OccEntry g_occ[64][26][8] = {};     // [0..15] kVariants, [16..19] kVariants64, [20..22] kVariantsU, [24..25] kVariants64W
 static int variant_occupancy(const Variant* v, int fi, size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
   const bool is64 = v >= kVariants64 && v < kVariants64 + 4;
   const bool isu = v >= kVariantsU && v < kVariantsU + 3;
-  OccEntry& e = g_occ[dev][isu ? 20 + (int)(v - kVariantsU) : is64 ? 16 + (int)(v - kVariants64) : (int)(v - kVariants)][fi];
+  const bool isw = v >= kVariants64W && v < kVariants64W + 2;
+  OccEntry& e = g_occ[dev][isw ? 24 + (int)(v - kVariants64W) : isu ? 20 + (int)(v - kVariantsU)
+                                 : is64 ? 16 + (int)(v - kVariants64) : (int)(v - kVariants)][fi];
   if (e.occ == 0 || e.smem != smem) {
     if (smem > 48 * 1024 && smem > e.smem_attr) {   // opt in to large dynamic shared memory
       cudaFuncSetAttribute(v->fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -983,7 +993,7 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   p.partials = reinterpret_cast<float*>(wp);
   const size_t smem = fused_smem_bytes(v, d->J, d->K, d->L0, d->L1);
   const bool gathered = idx != nullptr || (d->flags & CYTOF_FLAG_SAMPLE_IN_KERNEL);
-  const int fi = v64 ? (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + (d->J - 32 > 8 ? 4 : 0)
+  const int fi = v64 ? (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + ((d->J - 32 > 8 && d->J <= 48) ? 4 : 0)
                      : (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
   const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem));
   const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);

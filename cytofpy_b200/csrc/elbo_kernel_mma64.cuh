@@ -42,11 +42,15 @@ constexpr int kXNCJ = 6, kXNCK = 8;       // k-chunks of 8 over markers and over
 // tiles of the 4 warp PAIRS, double-buffered: A = [D_hi (64 rows) ; D_lo (64 rows)] x 8 cells, B = [g_hi ; g_lo]
 constexpr int kXUFloats = CYTOF_X_TMEM ? 16 + 4 * 2 * 2 * 1024 : 0;
 constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4 + kXUFloats;
+// WIDE instances (48 < J <= 64, NTP = 4: every cell takes a second full pass over markers 32..63): 64-marker tiles
+constexpr int kXDSW = 68, kXJSW = 64, kXMTJW = 4, kXNCJW = 8;
+constexpr int kXZFloatsW = (kXMTK * kXNCJW + kXMTJW * kXNCK) * 32 * 4 + kXUFloats;
 // c = F32, a = b = TF32, both K-major, N = 128, M = 128
 constexpr uint32_t kUmmaIdesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 // per warp (floats): D hi/lo [2][8][52] | g hi/lo [2][8][68] | A0/c1 [4][52] | y^2 [4][52] |
 // 1/S0,1/S1 [6 units][32] float2 | per-cell scalars [16] | y double buffer [2][4][48] | sum w d [6][32]
 constexpr int kXWarpFloats = 2 * 8 * kXDS + 2 * 8 * kXGS + 2 * kXT * kXDS + 6 * 32 * 2 + 16 + 2 * kXT * kXJS + 6 * 32;
+constexpr int kXWarpFloatsW = 2 * 8 * kXDSW + 2 * 8 * kXGS + 2 * kXT * kXDSW + 8 * 32 * 2 + 16 + 2 * kXT * kXJSW + 8 * 32;
 
 template <int LM0, int NC, int NPT>
 __device__ __forceinline__ void mix_forward(const float yv, const float mc0, const float mc1, const float nh2,
@@ -111,6 +115,13 @@ __global__ void __launch_bounds__(kXThreads, 1)
 elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   pdl_enter();
   constexpr int NC = LM0 + LM1, NPT = (NC + 1) / 2;
+  // NTP == 4 is the WIDE layout (48 < J <= 64); these shadow the namespace-scope constants of the narrow layout
+  constexpr bool WIDE = NTP == 4;
+  constexpr int kXDS = WIDE ? kXDSW : cytof::kXDS, kXJS = WIDE ? kXJSW : cytof::kXJS;
+  constexpr int kXMTJ = WIDE ? kXMTJW : cytof::kXMTJ, kXNCJ = WIDE ? kXNCJW : cytof::kXNCJ;
+  constexpr int kXZFloats = WIDE ? kXZFloatsW : cytof::kXZFloats, kXWarpFloats = WIDE ? kXWarpFloatsW : cytof::kXWarpFloats;
+  constexpr int NUX = WIDE ? 8 : 6;                          // rows of the per-unit tables sR / sW
+  static_assert(!WIDE || CYTOF_X_TMEM, "the WIDE layout keeps dZ in tensor memory");
   constexpr int CPT = kXT / NTP, TP = 32 / CPT;            // cells and (padded) tail markers per tail pass
   constexpr int NU = kXT + NTP;                             // mixture units (warp passes) per tile
   constexpr unsigned FULL = 0xffffffffu;
@@ -133,7 +144,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   float* sA = sGb + 2 * 8 * kXGS;                  // [4][kXDS] A0_j, later c1_j
   float* sY = sA + kXT * kXDS;                     // [4][kXDS] y_j^2
   float2* sR = reinterpret_cast<float2*>(sY + kXT * kXDS);   // [NU][32] (1/S0, 1/S1) per unit and lane
-  float* sS = reinterpret_cast<float*>(sR + 6 * 32);          // [0..3] fac rho, [4..7] fac (1-rho), [8..11] sc
+  float* sS = reinterpret_cast<float*>(sR + NUX * 32);        // [0..3] fac rho, [4..7] fac (1-rho), [8..11] sc
   float* sYb = sS + 16;                            // [2][4][kXJS] y rows
   float* sW = sYb + 2 * kXT * kXJS;                // [NU][32] sum_l w d per unit (imputation gradient)
   float* sred = smem;
@@ -506,9 +517,9 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     // ===== contraction 1: f^T[k, (n, hi|lo)] = Z^T . [D_hi | D_lo]^T (+ log W on the hi column)
     float fT[kXMTK][4];
     {
-      uint32_t rb[12];     // B fragments: block q = markers 4q..4q+3, column g = row g of the D tile
+      uint32_t rb[2 * kXNCJ];     // B fragments: block q = markers 4q..4q+3, column g = row g of the D tile
 #pragma unroll
-      for (int q4 = 0; q4 < 3; ++q4) {
+      for (int q4 = 0; q4 < kXNCJ / 2; ++q4) {
         uint32_t r4[4];
         ldsm_x4(sD + (lane & 7) * kXDS + 16 * q4 + 4 * (lane >> 3), r4);
 #pragma unroll
@@ -577,12 +588,22 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     float ra, ry = 0.f;
     {
       const float4 a4 = *reinterpret_cast<const float4*>(sA + t4 * kXDS + 4 * g);
-      const float2 a2 = *reinterpret_cast<const float2*>(sA + t4 * kXDS + 32 + 2 * g);
-      ra = ((a4.x + a4.y) + (a4.z + a4.w)) + (a2.x + a2.y);
+      if (WIDE) {     // tail columns 32..63: four per g
+        const float4 b4 = *reinterpret_cast<const float4*>(sA + t4 * kXDS + 32 + 4 * g);
+        ra = ((a4.x + a4.y) + (a4.z + a4.w)) + ((b4.x + b4.y) + (b4.z + b4.w));
+      } else {        // tail columns 32..47: two per g
+        const float2 a2 = *reinterpret_cast<const float2*>(sA + t4 * kXDS + 32 + 2 * g);
+        ra = ((a4.x + a4.y) + (a4.z + a4.w)) + (a2.x + a2.y);
+      }
       if (NOISY) {
         const float4 c4 = *reinterpret_cast<const float4*>(sY + t4 * kXDS + 4 * g);
-        const float2 c2 = *reinterpret_cast<const float2*>(sY + t4 * kXDS + 32 + 2 * g);
-        ry = ((c4.x + c4.y) + (c4.z + c4.w)) + (c2.x + c2.y);
+        if (WIDE) {
+          const float4 d4 = *reinterpret_cast<const float4*>(sY + t4 * kXDS + 32 + 4 * g);
+          ry = ((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w));
+        } else {
+          const float2 c2 = *reinterpret_cast<const float2*>(sY + t4 * kXDS + 32 + 2 * g);
+          ry = ((c4.x + c4.y) + (c4.z + c4.w)) + (c2.x + c2.y);
+        }
       }
     }
     {

@@ -39,8 +39,9 @@ extern "C" {
  * serves it decides the speed (per 1 M cells on one B200, profiles/README.md):
  *   J <= 32, K <= 32                  tensor-core kernel, mma.sync TF32 (cfg1-cfg4: 0.27 ms at J=32, K=30, L=5/5)
  *   J <= 48, K <= 64 otherwise        tensor-core kernel with dZ in tensor memory (cfg5: 0.85 ms at J=40, K=50, L=8/8;
- *                                     J <= 32 with K > 32 runs it with the marker lanes >= J masked)
- *   J > 48                            the first SIMT kernel: ~3.7x slower per cell than the tensor-core kernels */
+ *                                     J <= 32 with K > 32 runs it with the marker lanes >= J masked: 0.66 ms at J=32, K=50)
+ *   48 < J <= 64, L0,L1 <= 5          the same kernel in its 64-marker layout (0.86 ms at J=64, K=64, L=5/5)
+ *   48 < J <= 64 with L0 or L1 > 5    the first SIMT kernel: ~3x slower per cell than the tensor-core kernels */
 #define CYTOF_MAX_SAMPLES 32 /* I */
 #define CYTOF_MAX_J 64       /* markers  */
 #define CYTOF_MAX_K 64       /* features */

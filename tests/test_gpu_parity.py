@@ -151,6 +151,9 @@ def _random_problem(I, J, K, L0, L1, N, nan_rate, seed, model_noisy=True):
     dict(I=2, J=20, K=40, L0=3, L1=3, N=[70, 33]),       # J <= 32 with K > 32: the cfg5-shape kernel, main lanes masked
     dict(I=2, J=32, K=64, L0=5, L1=5, N=[64, 65]),
     dict(I=1, J=5, K=33, L0=8, L1=2, N=[50]),
+    dict(I=2, J=64, K=64, L0=5, L1=5, N=[64, 65]),       # 48 < J <= 64, L <= 5: the WIDE layout of the cfg5-shape kernel
+    dict(I=2, J=49, K=33, L0=3, L1=3, N=[41, 90]),
+    dict(I=3, J=56, K=10, L0=5, L1=2, N=[33, 7, 64]),
 ])
 @pytest.mark.parametrize('noisy', [True, False])
 def test_kernel_random_shapes(shape, noisy):
@@ -178,6 +181,8 @@ def test_kernel_random_shapes(shape, noisy):
     dict(I=2, J=48, K=33, L0=8, L1=5, N=[97, 40]),       # J at the kernel's maximum
     dict(I=2, J=30, K=50, L0=5, L1=5, N=[150, 77]),      # J <= 32 with K > 32 (16-byte rows: no, 120 B), masked main lanes
     dict(I=2, J=28, K=36, L0=3, L1=5, N=[90, 41]),       # the same with 16-byte aligned rows
+    dict(I=2, J=64, K=50, L0=5, L1=5, N=[150, 77]),      # WIDE layout (48 < J <= 64): second full marker pass per cell
+    dict(I=2, J=51, K=40, L0=4, L1=5, N=[90, 41]),       # WIDE, rows not 16-byte aligned
 ])
 @pytest.mark.parametrize('noisy', [True, False])
 @pytest.mark.parametrize('gather', [True, False])
@@ -300,7 +305,8 @@ def test_philox_mode_matches_oracle_on_emitted_noise_and_is_shard_invariant():
 @pytest.mark.parametrize('shape', [
     dict(I=2, J=32, K=30, L0=5, L1=3, N=[900, 700], mb=[300, 333]),      # tensor-core kernel, cfg3 shapes
     dict(I=2, J=40, K=50, L0=8, L1=8, N=[400, 300], mb=[130, 77]),       # cfg5-shape kernel (tail markers)
-    dict(I=2, J=50, K=20, L0=3, L1=4, N=[300, 200], mb=[90, 64]),        # first kernel (J > 48)
+    dict(I=2, J=50, K=20, L0=3, L1=4, N=[300, 200], mb=[90, 64]),        # WIDE layout (48 < J <= 64)
+    dict(I=2, J=50, K=20, L0=6, L1=4, N=[300, 200], mb=[90, 64]),        # first kernel (J > 48 with L > 5)
 ])
 def test_philox_mode_gathered_minibatch_is_keyed_by_position(shape):
     """In-kernel noise for a GATHERED minibatch: the draw of (cell, marker) is keyed by the cell's position in the
@@ -337,7 +343,8 @@ def test_philox_mode_gathered_minibatch_is_keyed_by_position(shape):
 @pytest.mark.parametrize('shape', [
     dict(I=3, J=32, K=30, L0=5, L1=3, N=[4000, 2500, 300], mb=[500, 500, 300]),     # tensor-core kernel; last sample whole
     dict(I=2, J=40, K=50, L0=8, L1=8, N=[900, 700], mb=[130, 77]),                   # cfg5-shape kernel
-    dict(I=2, J=50, K=20, L0=3, L1=4, N=[300, 200], mb=[90, 64]),                    # first kernel (J > 48)
+    dict(I=2, J=50, K=20, L0=3, L1=4, N=[300, 200], mb=[90, 64]),                    # WIDE layout (48 < J <= 64)
+    dict(I=2, J=50, K=20, L0=6, L1=4, N=[300, 200], mb=[90, 64]),                    # first kernel (J > 48 with L > 5)
     dict(I=2, J=20, K=12, L0=3, L1=3, N=[1000, 513], mb=[64, 512]),                  # rows narrower than 128 bytes
 ])
 @pytest.mark.parametrize('nan_rate', [0.0, 0.25])

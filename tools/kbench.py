@@ -16,7 +16,7 @@ from cytofpy_b200.model.engine import Batch, CellEngine  # noqa: E402
 
 SH = {'cfg1': (3, 2000, 32, 5, 3, 3), 'cfg2': (3, 40000, 32, 30, 5, 3), 'cfg4': (8, 125000, 32, 30, 5, 5),
       'cfg5': (8, 1250000, 40, 50, 8, 8), 'cfg5s': (8, 125000, 40, 50, 8, 8),
-      'j32k50': (8, 125000, 32, 50, 5, 5), 'l88': (8, 125000, 32, 30, 8, 8), 'l75': (8, 125000, 32, 30, 7, 5), 'j24k40': (8, 125000, 24, 40, 5, 3)}
+      'j32k50': (8, 125000, 32, 50, 5, 5), 'j64k64': (8, 125000, 64, 64, 5, 5), 'j56k40': (8, 125000, 56, 40, 5, 3), 'l88': (8, 125000, 32, 30, 8, 8), 'l75': (8, 125000, 32, 30, 7, 5), 'j24k40': (8, 125000, 24, 40, 5, 3)}
 
 
 def main():
