@@ -217,7 +217,8 @@ struct ElboParams {
 using KernelFn = void (*)(const ElboParams);
 // lidx: 0 = (3,3), 1 = (5,3), 2 = (5,5), 3 = (8,8) mixture sizes; fi = noisy + 2 * has_idx + 4 * no_missing
 KernelFn mma_kernel_fn(int lidx, int fi);
-// lidx: 0 = (5,5), 1 = (8,8); missing: imputation path compiled in; fi = noisy + 2 * has_idx + 4 * (tail passes - 1)
+// lidx: 0 = (5,5), 1 = (8,8), 2 = (5,5) in the WIDE layout (48 < J <= 64; fi = noisy + 2 * has_idx);
+// missing: imputation path compiled in; fi = noisy + 2 * has_idx + 4 * (tail passes - 1)
 KernelFn mma64_kernel_fn(int lidx, int missing, int fi);
 // CTA-wide tcgen05 kernel (elbo_kernel_umma.cuh): lidx 0 = (3,3), 1 = (5,3), 2 = (5,5); fi as for mma_kernel_fn
 KernelFn umma_kernel_fn(int lidx, int fi);

@@ -1,6 +1,7 @@
 // Tensor-core fused ELBO kernel for 32 < J <= 48 markers, K <= 64 features, L <= 8 components
-// (BASELINE cfg5: J = 40, K = 50, L = 8/8), and for J <= 32 markers with 32 < K <= 64 features (main lanes >= J are
-// masked, the tail pass runs empty).  MISSING = false compiles the imputation path out.
+// (BASELINE cfg5: J = 40, K = 50, L = 8/8), for J <= 32 markers with 32 < K <= 64 features (main lanes >= J are
+// masked, the tail pass runs empty), and -- NTP = 4, the WIDE layout -- for 48 < J <= 64 with L <= 5 (every cell takes a
+// second full pass over markers 32..63).  MISSING = false compiles the imputation path out.
 //
 // The first SIMT kernel needs 1,767 warp-instructions per cell at these shapes (bit-mask Z gating,
 // two markers per lane, register spills; profiles/README.md).  This kernel keeps the structure of
@@ -108,8 +109,9 @@ __device__ __forceinline__ float mix_backward(const float yv, const float mc0, c
   return WD ? fmaf(c0, y0, c1 * y1) - (lo2(wm) + hi2(wm)) : 0.f;
 }
 
-// NTP = tail passes per 4-cell tile: 1 (J - 32 <= 8: 4 cells x 8 tail markers per pass) or
-//                                    2 (J - 32 <= 16: 2 cells x 16 tail markers per pass)
+// NTP = tail passes per 4-cell tile: 1 (J - 32 <= 8: 4 cells x 8 tail markers per pass),
+//                                    2 (J - 32 <= 16: 2 cells x 16 tail markers per pass) or
+//                                    4 (J - 32 <= 32: 1 cell x 32 tail markers per pass; WIDE tile layout)
 template <int LM0, int LM1, bool NOISY, bool HAS_IDX, int NTP, bool MISSING>
 __global__ void __launch_bounds__(kXThreads, 1)
 elbo_fwdbwd_mma64_kernel(const ElboParams p) {

@@ -1,4 +1,5 @@
-// Instantiations of the tensor-core kernel for 32 < J <= 48, K <= 64 (csrc/elbo_kernel_mma64.cuh).
+// Instantiations of the tensor-core kernel for J <= 64, K <= 64 beyond the 8-cell-tile kernel's J, K <= 32
+// (csrc/elbo_kernel_mma64.cuh).
 #include "elbo_kernel_mma64.cuh"
 
 namespace cytof {
