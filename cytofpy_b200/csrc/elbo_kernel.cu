@@ -534,15 +534,15 @@ elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
     const bool valid = e < len;
     const float* src = P + off + (valid ? e : 0);
     double a = 0.0;
-    int b = b0 + warp;
-    for (; b + 24 < b1; b += 32) {           // 4 independent loads in flight
-      float v[4];
+    // 16 predicated loads in flight per lane: the 19 records per warp of a 148-CTA dZ section are 2 memory round
+    // trips (were 5 with 4 in flight + a serial remainder); adding 0.0f for the masked ones keeps the order fixed
+    for (int b = b0 + warp; b < b1; b += 128) {
+      float v[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(b + 8 * u) * pl.total);
+      for (int u = 0; u < 16; ++u) v[u] = (b + 8 * u < b1) ? __ldg(src + (size_t)(b + 8 * u) * pl.total) : 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a += (double)v[u];
+      for (int u = 0; u < 16; ++u) a += (double)v[u];
     }
-    for (; b < b1; b += 8) a += (double)__ldg(src + (size_t)b * pl.total);
     s_part[warp][lane] = a;
     __syncthreads();
     if (warp == 0 && valid) {
@@ -573,10 +573,10 @@ elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
         const int l = z1 ? sidx - L0 : sidx;
         const int off = (z1 ? pl.swd1 : pl.swd0) + l;
         int i = 0;
-        for (int bb = lane; bb < p.nblocks; bb += 128) {
-          float v[4], sg[4];
+        for (int bb = lane; bb < p.nblocks; bb += 256) {     // 8 records per lane in flight: one round trip up to 256 records
+          float v[8], sg[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int b = bb + 32 * u;
             const bool in = b < p.nblocks;
             while (in && i + 1 < I && b >= p.blk_begin[i + 1]) ++i;
@@ -584,7 +584,7 @@ elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
             sg[u] = __ldg(G + gl.sig + i);
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) r += (double)v[u] / ((double)sg[u] * (double)sg[u]);
+          for (int u = 0; u < 8; ++u) r += (double)v[u] / ((double)sg[u] * (double)sg[u]);
         }
         r = butterfly(r);
         t = (z1 ? bl.dmu1 : bl.dmu0) + l;
@@ -605,8 +605,14 @@ elbo_finalize_kernel(const ElboParams p, float* __restrict__ grad_block,
         else { r = a / (par * par * par) - (double)J * c / par; t = bl.dsig + i; }
       } else {                          // ll, log_qy
         const int which = sidx - (L0 + L1 + 2 * I);
-        for (int b = lane; b < p.nblocks; b += 32)
-          r += reinterpret_cast<const double*>(P + (size_t)b * pl.total + pl.dbl)[which];
+        for (int bb = lane; bb < p.nblocks; bb += 256) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            v[u] = (bb + 32 * u < p.nblocks) ? reinterpret_cast<const double*>(P + (size_t)(bb + 32 * u) * pl.total + pl.dbl)[which] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) r += v[u];
+        }
         r = butterfly(r);
         t = bl.total + which;
       }
@@ -754,7 +760,9 @@ struct Variant {
   bool records_alias;   // the final per-warp records reuse the main-loop shared memory
   int threads;          // CTA size (0 = kThreads)
   int smem_bytes;       // fixed dynamic shared memory size (0 = derived from the per-warp figures)
+  int split;            // blocks of the grid plan (= partial records) per CTA (0 = 1): kMmaSplit warp groups in the MMA variants
 };
+static int variant_split(const Variant* v) { return v->split ? v->split : 1; }
 static int variant_threads(const Variant* v) { return v->threads ? v->threads : kThreads; }
 #define CYTOF_VARIANT(a, b, jp, kp) \
   { a, b, jp, kp, (jp) * 32 + (kp) * 32, 0, { elbo_fwdbwd_kernel<a, b, jp, kp, false>, elbo_fwdbwd_kernel<a, b, jp, kp, true>, \
@@ -764,7 +772,7 @@ static int variant_threads(const Variant* v) { return v->threads ? v->threads : 
 #define CYTOF_FN8(f, ...) { f(__VA_ARGS__, 0), f(__VA_ARGS__, 1), f(__VA_ARGS__, 2), f(__VA_ARGS__, 3), \
                             f(__VA_ARGS__, 4), f(__VA_ARGS__, 5), f(__VA_ARGS__, 6), f(__VA_ARGS__, 7) }
 #define CYTOF_VARIANT_MMA(a, b, lidx) \
-  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, CYTOF_FN8(mma_kernel_fn, lidx), true }
+  { a, b, 1, 1, kMmaWarpFloats, kMmaZFloats, CYTOF_FN8(mma_kernel_fn, lidx), true, 0, 0, kMmaSplit }
 #ifndef CYTOF_MMA
 #define CYTOF_MMA 1   // 1: tensor-core kernel (elbo_kernel_mma.cuh) for J, K <= 32; 0: the first SIMT kernel (A/B builds)
 #endif
@@ -931,11 +939,13 @@ void fill_params(const cytof_desc* d, ElboParams* p) {
 
 // Splits the grid over samples so that a CTA never mixes samples: every non-empty sample gets
 // one CTA, the rest go one at a time to the sample with the most cells per CTA (min-max
-// optimal).  The total never exceeds SMs x resident CTAs/SM: exactly one wave, no tail.
-static int plan_grid(const cytof_desc* d, ElboParams* p, int occ) {
+// optimal).  The total never exceeds SMs x resident CTAs/SM: exactly one wave, no tail.  A "block" of the plan is
+// one partial record: a whole CTA, or one of the `split` warp groups of a CTA (MMA variants).
+static int plan_grid(const cytof_desc* d, ElboParams* p, int occ, int split, int threads) {
   const long long C = d->cell_begin[d->I];
-  const int cap = device_sm_count() * occ;
-  long long want = (C + (long long)kWarps * kMinCellsPerWarp - 1) / ((long long)kWarps * kMinCellsPerWarp);
+  const int cap = device_sm_count() * occ * split;
+  const long long bw = threads / 32 / split;        // warps per block
+  long long want = (C + bw * kMinCellsPerWarp - 1) / (bw * kMinCellsPerWarp);
   if (want > cap) want = cap;
   int n[CYTOF_MAX_SAMPLES];
   long long B[CYTOF_MAX_SAMPLES];
@@ -995,14 +1005,15 @@ int launch_fwdbwd(const cytof_desc* d, const float* y, const int32_t* idx, const
   const bool gathered = idx != nullptr || (d->flags & CYTOF_FLAG_SAMPLE_IN_KERNEL);
   const int fi = v64 ? (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + ((d->J - 32 > 8 && d->J <= 48) ? 4 : 0)
                      : (d->model_noisy ? 1 : 0) + (gathered ? 2 : 0) + ((d->flags & CYTOF_FLAG_NO_MISSING) ? 4 : 0);
-  const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem));
+  const int split = variant_split(v);
+  const int nblocks = plan_grid(d, &p, variant_occupancy(v, fi, smem), split, variant_threads(v));
   const PartialLayout pl = partial_layout(d->J, d->K, d->L0, d->L1);
   const size_t need = sizeof(float) * (size_t)pl.total * (size_t)nblocks + (wp - reinterpret_cast<uintptr_t>(workspace));
   if (need > workspace_bytes_) return CYTOF_EWORKSPACE;
   const BlockLayout bl = block_layout(d->I, d->J, d->K, d->L0, d->L1);
   if (nblocks > 0) {
     KernelFn fn = v->fn[fi];
-    *err = launch_pdl(fn, dim3(nblocks), dim3(variant_threads(v)), smem, stream, p);
+    *err = launch_pdl(fn, dim3((nblocks + split - 1) / split), dim3(variant_threads(v)), smem, stream, p);
     if (*err != cudaSuccess) return CYTOF_ECUDA;
   }
   const int nout = bl.total + 2;

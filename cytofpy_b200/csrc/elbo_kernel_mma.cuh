@@ -32,6 +32,18 @@ constexpr int kTileFloats = kTile * kTS;
 // per-warp shared memory: D, A0/c1, y^2, g tiles, 1/S0 and 1/S1, per-cell scalars, y double buffer
 constexpr int kMmaWarpFloats = 4 * kTileFloats + 2 * kTile * 32 + 32 + 2 * kTile * 32 + 12 * 32;   // sW: 12 rows (Philox staging)
 constexpr int kMmaZFloats = 2 * 8 * 32 * 4;     // A-fragment tables of Z^T and Z
+// A CTA's warps form kMmaSplit GROUPS; a group is what the host's grid plan calls a block: it owns a cell range of ONE
+// sample and writes one partial record.  Two groups of 4 warps per CTA halve the granularity of the split over the
+// samples (cfg4: 296 groups = 37 per sample exactly, where 148 CTAs split 19 / 18 and the slowest CTA carries 2.7 %
+// more cells than the mean).  MEASURED SLOWER (profiles/README.md, r2n: cfg4 0.2753 vs 0.2693 ms, 125 k cells 54.3 vs
+// 50.2 us, 6,000 cells 21.5 vs 19.5 us -- twice the records for the finalise kernel outweigh the balance), so the
+// default is one group = the whole CTA.
+#ifndef CYTOF_MMA_SPLIT
+#define CYTOF_MMA_SPLIT 1
+#endif
+constexpr int kMmaSplit = CYTOF_MMA_SPLIT;
+constexpr int kGroupWarps = kWarps / kMmaSplit;
+static_assert(kGroupWarps * kMmaSplit == kWarps && kGroupWarps >= 1, "groups must tile the CTA");
 
 
 // Packed fp32 through the CUDA 12.9 sm_100 intrinsics (FFMA2 / FADD2 / FMUL2 on float2): unlike
@@ -140,6 +152,12 @@ __device__ __forceinline__ void constexpr_pair_max(const int q, const float2 v, 
   else { M0 = fmaxf(M0, lo2(v)); M1 = fmaxf(M1, hi2(v)); }
 }
 
+#ifndef CYTOF_DZ_FLOAT
+#define CYTOF_DZ_FLOAT 1   // 1: the dZ MMAs are issued inside the backward / next-forward block (kernels without the imputation path); 2: in all kernels
+#endif
+#ifndef CYTOF_STAGGER_NS
+#define CYTOF_STAGGER_NS 0  // > 0: the upper half of the warps enters the loop this many ns late (de-phases the two warps of a scheduler)
+#endif
 #ifndef CYTOF_PIPELINE
 #define CYTOF_PIPELINE 1   // 1: phase B of a tile interleaved with phase A of the warp's next tile
 #endif
@@ -162,6 +180,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = warp / kGroupWarps, wg = warp - grp * kGroupWarps;     // record group of the warp, warp within it
+  const int vb = (int)blockIdx.x * kMmaSplit + grp;                       // the group's block of the grid plan
+  const bool live = vb < p.nblocks;                                       // an odd plan leaves the last group idle
   const int g = lane >> 2, t4 = lane & 3;                   // MMA fragment coordinates
   uint4* sZT = reinterpret_cast<uint4*>(smem);              // [mt][c][lane] A fragments of Z^T (k x j)
   uint4* sZ = sZT + 8 * 32;                                 // [mt][c][lane] A fragments of Z   (j x k)
@@ -179,9 +200,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 
   const int I = p.I, J = p.J, K = p.K, L0 = p.L0, L1 = p.L1;
   int i = 0;
-  while (i + 1 < I && (int)blockIdx.x >= p.blk_begin[i + 1]) ++i;
+  const int vbc = live ? vb : p.nblocks - 1;
+  while (i + 1 < I && vbc >= p.blk_begin[i + 1]) ++i;
   const int nb = p.blk_begin[i + 1] - p.blk_begin[i];
-  const int lb = (int)blockIdx.x - p.blk_begin[i];
+  const int lb = vbc - p.blk_begin[i];
   const long long cb = p.cell_begin[i];
   const long long Bi = p.cell_begin[i + 1] - cb;
   const long long row_base = p.row_base[i];
@@ -203,29 +225,32 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   // full-batch variants WITH the imputation path keep the request next to its wait: hoisting it there changed the
   // register allocation of the main loop (20 -> 40 bytes of spills) and cost 3.6 % at 30 % NaN.
   constexpr bool EARLY = !MISSING || (CYTOF_EARLY_IDX && HAS_IDX);
+  constexpr bool DZ_FLOAT = CYTOF_DZ_FLOAT == 2 || (CYTOF_DZ_FLOAT == 1 && !MISSING);
   if (EARLY) {
     const GlobalsLayout glp = globals_layout(I, J, K, L0, L1);
-    const float* base = G;
-    int nfl = L0 + L1 + I;
-    switch (warp) {
-      case 1: base = G + glp.le0 + i * J * L0; nfl = J * L0; break;
-      case 2: base = G + glp.le1 + i * J * L1; nfl = J * L1; break;
-      case 3: base = G + glp.lw + i * K; nfl = K; break;
-      case 4: base = G + glp.eps; nfl = 4 * I; break;
-      case 5: base = G + glp.vm + i * J; nfl = J; break;
-      case 6: base = G + glp.vls + i * J; nfl = J; break;
-      case 7: base = reinterpret_cast<const float*>(p.zmask); nfl = 2 * J; break;
-      default: break;
+    for (int piece = wg; piece < 8; piece += kGroupWarps) {     // the group's warps share the 8 slices of its sample
+      const float* base = G;
+      int nfl = L0 + L1 + I;
+      switch (piece) {
+        case 1: base = G + glp.le0 + i * J * L0; nfl = J * L0; break;
+        case 2: base = G + glp.le1 + i * J * L1; nfl = J * L1; break;
+        case 3: base = G + glp.lw + i * K; nfl = K; break;
+        case 4: base = G + glp.eps; nfl = 4 * I; break;
+        case 5: base = G + glp.vm + i * J; nfl = J; break;
+        case 6: base = G + glp.vls + i * J; nfl = J; break;
+        case 7: base = reinterpret_cast<const float*>(p.zmask); nfl = 2 * J; break;
+        default: break;
+      }
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)127, a1 = reinterpret_cast<uintptr_t>(base + nfl);
+      for (uintptr_t q = a0 + 128u * lane; q < a1; q += 128u * 32u) asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
     }
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)127, a1 = reinterpret_cast<uintptr_t>(base + nfl);
-    for (uintptr_t q = a0 + 128u * lane; q < a1; q += 128u * 32u) asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
   }
   // ---------------- stream the cells of this CTA, 8 per warp iteration ----------------
   const int32_t* __restrict__ idx = p.idx + (HAS_IDX ? (cb + c_lo) : 0);
   const float* __restrict__ ysamp = p.y + (size_t)row_base * J;
-  const int ncell = (int)(c_hi - c_lo);
+  const int ncell = live ? (int)(c_hi - c_lo) : 0;
   const int first_row = (int)c_lo;            // full batch: row = c_lo + cell
-  constexpr int STRIDE = kWarps * kTile;
+  constexpr int STRIDE = kGroupWarps * kTile;
   const bool vec16 = J == 32 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;   // 128-byte rows
 
   // y rows of the tile starting at cell tn -> sYb[b]; rows past the end of the range and lanes
@@ -269,7 +294,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     cp_async_commit();
   };
 
-  if (EARLY && warp * kTile < ncell) issue_tile(warp * kTile, 0);
+  if (EARLY && wg * kTile < ncell) issue_tile(wg * kTile, 0);
 
   // ---------------- Z fragment tables (once per CTA) ----------------
   {
@@ -486,11 +511,47 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     if (MISSING && amask) sW[u * 32 + lane] = fmaf(c0, y0, c1 * y1) - (lo2(wm) + hi2(wm));
   };
 
+  // contraction 3: dZ[j, k] += D^T . g over the 8 cells of the tile (tensor cores).  Nothing in the tile's backward
+  // depends on it.  CYTOF_DZ_FLOAT = 1 issues it INSIDE the basic block of the mixture backward / next forward, so that
+  // its 24 HMMA (252 tensor-pipe cycles per tile) overlap this warp's own FMA / MUFU work instead of stalling the warp.
+  struct DzOps { uint4 ah[2], al2[2]; float gl4[4], gh4[4]; };
+  auto dz_load = [&](DzOps& o) {       // operands out of this tile's D / e tiles (cross-lane reads: before the tiles are rewritten)
+    const float4 d_lo = *reinterpret_cast<const float4*>(sD + t4 * kTS + 4 * g);        // cell t4,   markers 4g..4g+3
+    const float4 d_hi = *reinterpret_cast<const float4*>(sD + (t4 + 4) * kTS + 4 * g);  // cell t4+4
+    const float4 e_lo = *reinterpret_cast<const float4*>(sG + t4 * kTS + 4 * g);        // cell t4,   features 4g..4g+3
+    const float4 e_hi = *reinterpret_cast<const float4*>(sG + (t4 + 4) * kTS + 4 * g);
+    const float sca = sS[16 + t4], scb = sS[16 + t4 + 4];
+    const float dl[4] = {d_lo.x, d_lo.y, d_lo.z, d_lo.w}, dh[4] = {d_hi.x, d_hi.y, d_hi.z, d_hi.w};
+    o.gl4[0] = sca * e_lo.x; o.gl4[1] = sca * e_lo.y; o.gl4[2] = sca * e_lo.z; o.gl4[3] = sca * e_lo.w;
+    o.gh4[0] = scb * e_hi.x; o.gh4[1] = scb * e_hi.y; o.gh4[2] = scb * e_hi.z; o.gh4[3] = scb * e_hi.w;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {   // rows g / g+8 of m-tile mt = markers 4g+2mt / 4g+2mt+1
+      split_tf32(dl[2 * mt], o.ah[mt].x, o.al2[mt].x);
+      split_tf32(dl[2 * mt + 1], o.ah[mt].y, o.al2[mt].y);
+      split_tf32(dh[2 * mt], o.ah[mt].z, o.al2[mt].z);
+      split_tf32(dh[2 * mt + 1], o.ah[mt].w, o.al2[mt].w);
+    }
+  };
+  auto dz_mma = [&](const DzOps& o) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {   // column g of n-tile nt = feature 4g+nt
+      uint32_t b0h, b0l, b1h, b1l;
+      split_tf32(o.gl4[nt], b0h, b0l);
+      split_tf32(o.gh4[nt], b1h, b1l);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_tf32(dZ[mt][nt], o.ah[mt], b0h, b1h);
+        mma_tf32(dZ[mt][nt], o.ah[mt], b0l, b1l);
+        mma_tf32(dZ[mt][nt], o.al2[mt], b0h, b1h);
+      }
+    }
+  };
+
 #ifdef CYTOF_PHASE_CLOCKS
   long long clkS = 0, clkBA = 0;
   int ntiles = 0;
 #endif
-  int t0 = warp * kTile;
+  int t0 = wg * kTile;
   int cur = 0;
   unsigned missmask = 0u, anymask = 0u;
 #ifdef CYTOF_STAMPS
@@ -514,6 +575,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     if (t0 + STRIDE < ncell) issue_tile(t0 + STRIDE, 1);
   }
   __syncthreads();   // Z tables visible
+#if CYTOF_STAGGER_NS > 0
+  if (warp >= kWarps / 2) __nanosleep(CYTOF_STAGGER_NS);
+#endif
 
 #ifdef CYTOF_STAMPS
   stamp_t[2] = stamp_now();
@@ -676,38 +740,10 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       sA[(ca + 1) * kTS + 16 * mt + g + 8] = sc2[1] * cT[mt][3];
     }
 
-    // ================= contraction 3: dZ[j, k] += D^T . g over the 8 cells (tensor cores) =================
-    // issued last: nothing in this tile's backward depends on it
-    {
-      const float4 d_lo = *reinterpret_cast<const float4*>(sD + t4 * kTS + 4 * g);        // cell t4,   markers 4g..4g+3
-      const float4 d_hi = *reinterpret_cast<const float4*>(sD + (t4 + 4) * kTS + 4 * g);  // cell t4+4
-      const float4 e_lo = *reinterpret_cast<const float4*>(sG + t4 * kTS + 4 * g);        // cell t4,   features 4g..4g+3
-      const float4 e_hi = *reinterpret_cast<const float4*>(sG + (t4 + 4) * kTS + 4 * g);
-      const float sca = sS[16 + t4], scb = sS[16 + t4 + 4];
-      const float dl[4] = {d_lo.x, d_lo.y, d_lo.z, d_lo.w}, dh[4] = {d_hi.x, d_hi.y, d_hi.z, d_hi.w};
-      const float gl4[4] = {sca * e_lo.x, sca * e_lo.y, sca * e_lo.z, sca * e_lo.w};
-      const float gh4[4] = {scb * e_hi.x, scb * e_hi.y, scb * e_hi.z, scb * e_hi.w};
-      uint4 ah[2], al2[2];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {   // rows g / g+8 of m-tile mt = markers 4g+2mt / 4g+2mt+1
-        split_tf32(dl[2 * mt], ah[mt].x, al2[mt].x);
-        split_tf32(dl[2 * mt + 1], ah[mt].y, al2[mt].y);
-        split_tf32(dh[2 * mt], ah[mt].z, al2[mt].z);
-        split_tf32(dh[2 * mt + 1], ah[mt].w, al2[mt].w);
-      }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {   // column g of n-tile nt = feature 4g+nt
-        uint32_t b0h, b0l, b1h, b1l;
-        split_tf32(gl4[nt], b0h, b0l);
-        split_tf32(gh4[nt], b1h, b1l);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          mma_tf32(dZ[mt][nt], ah[mt], b0h, b1h);
-          mma_tf32(dZ[mt][nt], ah[mt], b0l, b1l);
-          mma_tf32(dZ[mt][nt], al2[mt], b0h, b1h);
-        }
-      }
-    }
+    // ================= contraction 3: dZ += D^T . g (tensor cores) =================
+    DzOps dzo;
+    dz_load(dzo);
+    if (!DZ_FLOAT) dz_mma(dzo);     // issued last in the stage: nothing in this tile's backward depends on it
     __syncwarp();
 
 
@@ -725,6 +761,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       cp_async_wait<0>();
       __syncwarp();
       if (MISSING) prepass(t0 + STRIDE, cur ^ 1, miss_n, any_n);
+      if (DZ_FLOAT) dz_mma(dzo);
 #if CYTOF_PIPELINE
       phase_b(0, ycur, missmask, anymask);
       AState prev = phase_a1(0, ynxt, miss_n);
@@ -749,6 +786,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       phase_a2(kTile - 1, prev);
 #endif
     } else {
+      if (DZ_FLOAT) dz_mma(dzo);
 #pragma unroll
       for (int u = 0; u < kTile; ++u) phase_b(u, ycur, missmask, anymask);
     }
@@ -870,18 +908,23 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
 #ifdef CYTOF_STAMPS
   stamp_t[4] = stamp_now();
 #endif
-  float* out = p.partials + (size_t)blockIdx.x * pl.total;
-  for (int t = threadIdx.x; t < pl.total; t += kThreads) {
-    if (t >= pl.dbl && t < pl.dbl + 4) continue;
-    float a = 0.f;
+  // every group adds the records of its own warps (fixed order) and stores the record of its block
+  float* out = p.partials + (size_t)vbc * pl.total;
+  const float* gred = sred + grp * kGroupWarps * pl.total;
+  const int gtid = (int)threadIdx.x - grp * (kGroupWarps * 32);
+  if (live) {
+    for (int t = gtid; t < pl.total; t += kGroupWarps * 32) {
+      if (t >= pl.dbl && t < pl.dbl + 4) continue;
+      float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) a += sred[w * pl.total + t];
-    out[t] = a;
-  }
-  if (threadIdx.x < 2) {
-    double a = 0.0;
-    for (int w = 0; w < kWarps; ++w) a += reinterpret_cast<const double*>(sred + w * pl.total + pl.dbl)[threadIdx.x];
-    reinterpret_cast<double*>(out + pl.dbl)[threadIdx.x] = a;
+      for (int w = 0; w < kGroupWarps; ++w) a += gred[w * pl.total + t];
+      out[t] = a;
+    }
+    if (gtid < 2) {
+      double a = 0.0;
+      for (int w = 0; w < kGroupWarps; ++w) a += reinterpret_cast<const double*>(gred + w * pl.total + pl.dbl)[gtid];
+      reinterpret_cast<double*>(out + pl.dbl)[gtid] = a;
+    }
   }
 #ifdef CYTOF_STAMPS
   stamp_t[5] = stamp_now();
