@@ -17,7 +17,11 @@
 //     exact fp32 remainder), and the products hi.Z + lo.Z (hi.hi + hi.lo + lo.hi for dZ) are
 //     accumulated in fp32, so the result carries ~22 mantissa bits: the 1e-4 / 1e-5 parity bars
 //     hold (single-pass TF32 would not);
-//   * streams y with cp.async (LDGSTS) into a per-warp double buffer one tile ahead.
+//   * streams y with cp.async (LDGSTS) into a per-warp double buffer one tile ahead;
+//   * issues the 24 HMMA of the dZ contraction inside the long basic block of the mixture backward / next forward
+//     (full-batch kernels without the imputation path), where the tensor pipe is otherwise idle: the contraction stage
+//     is a latency chain (ldmatrix -> HMMA chain -> 3 shuffle rounds -> ex2 -> STS -> ldmatrix -> HMMA chain) that only
+//     the scheduler's other warp can cover, so every tensor-pipe cycle taken out of it counts (round 2, r2n: -3.8 %).
 // Per-cell scalars (logsumexp over K, noisy class) are evaluated in the accumulator layout of the
 // first MMA (thread (g,t) owns cells 2t, 2t+1 and features g, g+8, g+16, g+24).
 #pragma once
@@ -70,17 +74,9 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4 a, const uin
 }
 // x = hi + lo with hi = x rounded to TF32 (round half away) and lo the exact remainder, truncated
 // to TF32 (the truncation error is <= 2^-21 |x| and follows the sign of lo, i.e. it is unbiased)
-#ifndef CYTOF_SPLIT_TRUNC
-#define CYTOF_SPLIT_TRUNC 0   // 1: hi by truncation, lo passed raw (the MMA ignores the low 13 bits)
-#endif
 __device__ __forceinline__ void split_tf32(const float x, uint32_t& hi, uint32_t& lo) {
-#if CYTOF_SPLIT_TRUNC
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-#else
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
-#endif
 }
 // split for operands the tensor core reads from shared memory (tcgen05 kind::tf32 uses the upper 19
 // bits of each fp32 word): hi = x truncated to TF32, lo = the exact remainder, stored as is
@@ -153,14 +149,25 @@ __device__ __forceinline__ void constexpr_pair_max(const int q, const float2 v, 
 }
 
 #ifndef CYTOF_DZ_FLOAT
-#define CYTOF_DZ_FLOAT 1   // 1: the dZ MMAs are issued inside the backward / next-forward block (kernels without the imputation path); 2: in all kernels
+#define CYTOF_DZ_FLOAT 1   // 1: the dZ MMAs are issued inside the backward / next-forward block (full-batch kernels without the imputation path); 2: in all kernels; 0: at the end of the contraction stage
 #endif
-#ifndef CYTOF_STAGGER_NS
-#define CYTOF_STAGGER_NS 0  // > 0: the upper half of the warps enters the loop this many ns late (de-phases the two warps of a scheduler)
+#ifndef CYTOF_A2_SKEW
+#define CYTOF_A2_SKEW 2    // the log / reciprocal half of the forward runs this many cells behind the ex2 half
 #endif
-#ifndef CYTOF_PIPELINE
-#define CYTOF_PIPELINE 1   // 1: phase B of a tile interleaved with phase A of the warp's next tile
-#endif
+// maxima of mixture 0 (components [0, LM0)) and mixture 1 ([LM0, NC)) of the packed list v, max3 over runs of the flat list
+template <int LM0, int NC, int NPT>
+__device__ __forceinline__ void flat_max(const float2 (&v)[NPT], float& M0, float& M1) {
+  auto at = [&](const int x) -> float { return (x & 1) ? hi2(v[x >> 1]) : lo2(v[x >> 1]); };
+#pragma unroll
+  for (int z = 0; z < 2; ++z) {
+    const int a = z ? LM0 : 0, b = z ? NC : LM0;
+    float m = at(a);
+#pragma unroll
+    for (int x = a + 1; x < b; x += 2) m = (x + 1 < b) ? max3(m, at(x), at(x + 1)) : fmaxf(m, at(x));
+    (z ? M1 : M0) = m;
+  }
+}
+
 
 // MISSING = false is the caller's promise (cytof_desc.flags & CYTOF_FLAG_NO_MISSING) that y holds
 // no NaN: the imputation pre-pass and the d/dy chain are compiled out.
@@ -180,9 +187,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = warp / kGroupWarps, wg = warp - grp * kGroupWarps;     // record group of the warp, warp within it
+  const int grp = kMmaSplit == 1 ? 0 : warp / kGroupWarps, wg = warp - grp * kGroupWarps;     // record group of the warp, warp within it
   const int vb = (int)blockIdx.x * kMmaSplit + grp;                       // the group's block of the grid plan
-  const bool live = vb < p.nblocks;                                       // an odd plan leaves the last group idle
+  const bool live = kMmaSplit == 1 || vb < p.nblocks;                     // an odd plan leaves the last group idle
   const int g = lane >> 2, t4 = lane & 3;                   // MMA fragment coordinates
   uint4* sZT = reinterpret_cast<uint4*>(smem);              // [mt][c][lane] A fragments of Z^T (k x j)
   uint4* sZ = sZT + 8 * 32;                                 // [mt][c][lane] A fragments of Z   (j x k)
@@ -225,7 +232,9 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   // full-batch variants WITH the imputation path keep the request next to its wait: hoisting it there changed the
   // register allocation of the main loop (20 -> 40 bytes of spills) and cost 3.6 % at 30 % NaN.
   constexpr bool EARLY = !MISSING || (CYTOF_EARLY_IDX && HAS_IDX);
-  constexpr bool DZ_FLOAT = CYTOF_DZ_FLOAT == 2 || (CYTOF_DZ_FLOAT == 1 && !MISSING);
+  // (the kernels with the imputation path and the gathered ones spill when the MMAs move: r2n / r2u in profiles/README.md)
+  constexpr bool DZ_FLOAT = CYTOF_DZ_FLOAT == 2 || (CYTOF_DZ_FLOAT == 1 && !MISSING && !HAS_IDX);
+  constexpr int SKEW = CYTOF_A2_SKEW;
   if (EARLY) {
     const GlobalsLayout glp = globals_layout(I, J, K, L0, L1);
     for (int piece = wg; piece < 8; piece += kGroupWarps) {     // the group's warps share the 8 slices of its sample
@@ -438,9 +447,11 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   const float2 nh = bcp(nh2);
 
   // mixture log-densities of cell u, forward (Model.py:223-233), log2 domain, component pairs.
-  // Two halves: a1 issues the 10 ex2 of the cell; a2 (called one cell later in the loops below, so
-  // that the MUFU pipe already works on the next cell's exponentials while the sums of this one
-  // settle) takes the logs / reciprocal and writes the tiles.
+  // Two halves: a1 issues the 10 ex2 of the cell; a2 (called CYTOF_A2_SKEW = 2 cells later in the main loop, so
+  // that the MUFU pipe already works on the next cells' exponentials while the sums of this one
+  // settle; r2q: skew 0 / 1 / 2 / 3 = 0.2776 / 0.2549 / 0.2510 / 0.2571 ms per 1 M cells) takes the logs / reciprocal
+  // and writes the tiles.  The component maxima run over the FLAT list (flat_max: 4 instead of 6 FMNMX3 per cell at
+  // L = 5 / 5, on the chain in front of the ex2: r2p, -3.8 %).
   struct AState { float S0, S1, B0, B1, yy; };
   auto phase_a1 = [&](const int u, const float* src, const unsigned mmask) -> AState {
     const float x = src[u * 32 + lane];
@@ -454,8 +465,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       v[q] = fma2(be[q], lo1 ? Y11 : (hi1 ? Y01 : Y00), al[q]);
     }
     float M0 = kNegBig, M1 = kNegBig;
-#pragma unroll
-    for (int q = 0; q < NPT; ++q) constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
+    flat_max<LM0, NC, NPT>(v, M0, M1);
     const float2 M00 = bcp(M0), M11 = bcp(M1), M01 = mkp(M0, M1);
     float2 s0 = bcp(0.f), s1 = bcp(0.f);
     float s0x = 0.f, s1x = 0.f;
@@ -575,9 +585,6 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
     if (t0 + STRIDE < ncell) issue_tile(t0 + STRIDE, 1);
   }
   __syncthreads();   // Z tables visible
-#if CYTOF_STAGGER_NS > 0
-  if (warp >= kWarps / 2) __nanosleep(CYTOF_STAGGER_NS);
-#endif
 
 #ifdef CYTOF_STAMPS
   stamp_t[2] = stamp_now();
@@ -585,7 +592,7 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
   for (; t0 < ncell; t0 += STRIDE, cur ^= 1) {
     const int nvalid = min(kTile, ncell - t0);
     const bool has_next = t0 + STRIDE < ncell;
-    __syncwarp();
+    __syncwarp();      // logically redundant (the iteration ends with one), but without it ptxas schedules the stage 6 % slower (profiles/README.md, r2s)
 #ifdef CYTOF_PHASE_CLOCKS
     const long long ck0 = clock64();
 #endif
@@ -762,29 +769,18 @@ elbo_fwdbwd_mma_kernel(const ElboParams p) {
       __syncwarp();
       if (MISSING) prepass(t0 + STRIDE, cur ^ 1, miss_n, any_n);
       if (DZ_FLOAT) dz_mma(dzo);
-#if CYTOF_PIPELINE
-      phase_b(0, ycur, missmask, anymask);
-      AState prev = phase_a1(0, ynxt, miss_n);
+      {
+        // cell u: backward of this tile, first forward half of the next tile, second forward half CYTOF_A2_SKEW cells late
+        AState st[kTile];
 #pragma unroll
-      for (int u = 1; u < kTile; ++u) {
-        phase_b(u, ycur, missmask, anymask);
-        const AState now = phase_a1(u, ynxt, miss_n);
-        phase_a2(u - 1, prev);
-        prev = now;
+        for (int u = 0; u < kTile + SKEW; ++u) {
+          if (u < kTile) {
+            phase_b(u, ycur, missmask, anymask);
+            st[u] = phase_a1(u, ynxt, miss_n);
+          }
+          if (u >= SKEW) phase_a2(u - SKEW, st[u - SKEW]);
+        }
       }
-      phase_a2(kTile - 1, prev);
-#else
-#pragma unroll
-      for (int u = 0; u < kTile; ++u) phase_b(u, ycur, missmask, anymask);
-      AState prev = phase_a1(0, ynxt, miss_n);
-#pragma unroll
-      for (int u = 1; u < kTile; ++u) {
-        const AState now = phase_a1(u, ynxt, miss_n);
-        phase_a2(u - 1, prev);
-        prev = now;
-      }
-      phase_a2(kTile - 1, prev);
-#endif
     } else {
       if (DZ_FLOAT) dz_mma(dzo);
 #pragma unroll

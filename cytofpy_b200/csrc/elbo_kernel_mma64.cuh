@@ -25,6 +25,9 @@
 
 namespace cytof {
 
+#ifndef CYTOF_X_A2_SKEW
+#define CYTOF_X_A2_SKEW 2   // the log / reciprocal half of a mixture unit runs this many units behind its ex2 half (r2t: cfg5 0.849 -> 0.845 ms, J = 64 0.856 -> 0.837 ms, J = 32 / K = 50 0.660 -> 0.663 ms per 1 M cells)
+#endif
 #ifndef CYTOF_X_NOGUARD
 #define CYTOF_X_NOGUARD 1   // 1 (measured faster): always run the full 4x6 / 3x8 MMA grids (padding is zero in the Z tables)
 #endif
@@ -66,8 +69,7 @@ __device__ __forceinline__ void mix_forward(const float yv, const float mc0, con
     v[q] = fma2(be[q], lo1 ? Y11 : (hi1 ? Y01 : Y00), al[q]);
   }
   float M0 = kNegBig, M1 = kNegBig;
-#pragma unroll
-  for (int q = 0; q < NPT; ++q) constexpr_pair_max<LM0, NC>(q, v[q], M0, M1);
+  flat_max<LM0, NC, NPT>(v, M0, M1);      // 2 FMNMX3 per 5 components (3 over the packed pairs)
   const float2 M00 = bcp(M0), M11 = bcp(M1), M01 = mkp(M0, M1);
   float2 s0 = bcp(0.f), s1 = bcp(0.f);
   float s0x = 0.f, s1x = 0.f;
@@ -730,16 +732,15 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       cp_async_wait<0>();
       __syncwarp();
       if (MISSING) prepass(r + 1, b ^ 1, mm_n, tm_n, am_n);
-      phase_b(0, ycur, mmask, tmask, amask);
-      AState prev = phase_a1(0, ynxt, mm_n, tm_n);
+      AState st[NU];      // the log / reciprocal half of unit un runs CYTOF_X_A2_SKEW units behind its ex2 half
 #pragma unroll
-      for (int un = 1; un < NU; ++un) {
-        phase_b(un, ycur, mmask, tmask, amask);
-        const AState now = phase_a1(un, ynxt, mm_n, tm_n);
-        phase_a2(un - 1, prev, b ^ 1);
-        prev = now;
+      for (int un = 0; un < NU + CYTOF_X_A2_SKEW; ++un) {
+        if (un < NU) {
+          phase_b(un, ycur, mmask, tmask, amask);
+          st[un] = phase_a1(un, ynxt, mm_n, tm_n);
+        }
+        if (un >= CYTOF_X_A2_SKEW) phase_a2(un - CYTOF_X_A2_SKEW, st[un - CYTOF_X_A2_SKEW], b ^ 1);
       }
-      phase_a2(NU - 1, prev, b ^ 1);
     } else {
 #pragma unroll
       for (int un = 0; un < NU; ++un) phase_b(un, ycur, mmask, tmask, amask);

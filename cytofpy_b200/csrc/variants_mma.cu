@@ -10,7 +10,11 @@ namespace cytof {
     elbo_fwdbwd_mma_kernel<a, b, false, true, false>, elbo_fwdbwd_mma_kernel<a, b, true, true, false> }
 
 KernelFn mma_kernel_fn(int lidx, int fi) {
+#ifdef CYTOF_TUNE_ONLY55     // tuning builds (tools/kvariants.py): only the L = 5/5 kernels are compiled; the other rows must not be used
+  static const KernelFn table[4][8] = { CYTOF_MMA_ROW(5, 5), CYTOF_MMA_ROW(5, 5), CYTOF_MMA_ROW(5, 5), CYTOF_MMA_ROW(5, 5) };
+#else
   static const KernelFn table[4][8] = { CYTOF_MMA_ROW(3, 3), CYTOF_MMA_ROW(5, 3), CYTOF_MMA_ROW(5, 5), CYTOF_MMA_ROW(8, 8) };
+#endif
   return table[lidx][fi];
 }
 

@@ -2,8 +2,8 @@
 
     python tools/kvariants.py name:DEF1=V,DEF2=V ...      ->  cytofpy_b200/_C/libv_<name>.so
 
-Only the translation units that see the tuning macros of the J, K <= 32 kernel (variants_mma.cu, elbo_kernel.cu) are
-recompiled; the other objects are those of the default build."""
+Only the translation unit that sees the tuning macros is recompiled (variants_mma.cu; variants_mma64.cu for CYTOF_X_*
+macros; elbo_kernel.cu as well for CYTOF_MMA_SPLIT); the other objects are those of the default build."""
 import os
 import subprocess
 import sys
@@ -24,7 +24,9 @@ def one(spec):
     objs = []
     for src in b.SOURCES:
         stem = os.path.splitext(src)[0]
-        if src in TUNED:
+        x64 = any(d.startswith('CYTOF_X_') for d in defines)
+        if (src == 'variants_mma.cu' and not x64) or (src == 'variants_mma64.cu' and x64) or \
+                (src == 'elbo_kernel.cu' and any('SPLIT' in d for d in defines)):
             obj = os.path.join(obj_dir, stem + '.o')
             r = subprocess.run([b._nvcc()] + b.NVCC_FLAGS + ['-D' + d for d in defines] + ['-c', '-o', obj, os.path.join(b.CSRC, src)],
                                capture_output=True, text=True)
@@ -42,6 +44,6 @@ def one(spec):
 
 if __name__ == '__main__':
     b.build()        # default objects first
-    with ThreadPoolExecutor(max_workers=3) as pool:
+    with ThreadPoolExecutor(max_workers=7) as pool:
         for o in pool.map(one, sys.argv[1:]):
             print(o)
