@@ -28,6 +28,9 @@ namespace cytof {
 #ifndef CYTOF_X_A2_SKEW
 #define CYTOF_X_A2_SKEW 2   // the log / reciprocal half of a mixture unit runs this many units behind its ex2 half (r2t: cfg5 0.849 -> 0.845 ms, J = 64 0.856 -> 0.837 ms, J = 32 / K = 50 0.660 -> 0.663 ms per 1 M cells)
 #endif
+#ifndef CYTOF_X_ZPF
+#define CYTOF_X_ZPF 6       // A fragments of Z / Z^T requested this many MMAs ahead (r2y: J=32, K=50, L=5/5 0.6625 -> 0.6485 ms per 1 M cells with 6, 0.6535 with 4; the L=8/8 instances compile to the same code either way)
+#endif
 #ifndef CYTOF_X_NOGUARD
 #define CYTOF_X_NOGUARD 1   // 1 (measured faster): always run the full 4x6 / 3x8 MMA grids (padding is zero in the Z tables)
 #endif
@@ -535,6 +538,20 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
         fT[mt][2] = lwk[2 * mt + 1];
         fT[mt][1] = fT[mt][3] = 0.f;
       }
+#if CYTOF_X_ZPF > 0 && CYTOF_X_NOGUARD
+      {   // the A fragments of Z^T are requested CYTOF_X_ZPF MMAs ahead of their use (each feeds ONE MMA here)
+        constexpr int NT = kXNCJ * kXMTK, PF = CYTOF_X_ZPF;
+        uint4 zq[PF];
+#pragma unroll
+        for (int t = 0; t < PF; ++t) zq[t] = sZT[((t % kXMTK) * kXNCJ + t / kXMTK) * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint4 a = zq[t % PF];
+          if (t + PF < NT) zq[t % PF] = sZT[(((t + PF) % kXMTK) * kXNCJ + (t + PF) / kXMTK) * 32 + lane];
+          mma_tf32(fT[t % kXMTK], a, rb[2 * (t / kXMTK)], rb[2 * (t / kXMTK) + 1]);
+        }
+      }
+#else
 #pragma unroll
       for (int c = 0; c < kXNCJ; ++c) {
         if (CYTOF_X_NOGUARD || c < ncj) {
@@ -543,6 +560,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
             if (CYTOF_X_NOGUARD || mt < mtk) mma_tf32(fT[mt], sZT[(mt * kXNCJ + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
         }
       }
+#endif
     }
     float f[8];
 #pragma unroll
@@ -578,6 +596,20 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       }
 #pragma unroll
       for (int mt = 0; mt < kXMTJ; ++mt) cT[mt][0] = cT[mt][1] = cT[mt][2] = cT[mt][3] = 0.f;
+#if CYTOF_X_ZPF > 0 && CYTOF_X_NOGUARD
+      {
+        constexpr int NT = kXNCK * kXMTJ, PF = CYTOF_X_ZPF;
+        uint4 zq[PF];
+#pragma unroll
+        for (int t = 0; t < PF; ++t) zq[t] = sZ[((t % kXMTJ) * kXNCK + t / kXMTJ) * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint4 a = zq[t % PF];
+          if (t + PF < NT) zq[t % PF] = sZ[(((t + PF) % kXMTJ) * kXNCK + (t + PF) / kXMTJ) * 32 + lane];
+          mma_tf32(cT[t % kXMTJ], a, rb[2 * (t / kXMTJ)], rb[2 * (t / kXMTJ) + 1]);
+        }
+      }
+#else
 #pragma unroll
       for (int c = 0; c < kXNCK; ++c) {
         if (CYTOF_X_NOGUARD || c < nck) {
@@ -586,6 +618,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
             if (CYTOF_X_NOGUARD || mt < mtj) mma_tf32(cT[mt], sZ[(mt * kXNCK + c) * 32 + lane], rb[2 * c], rb[2 * c + 1]);
         }
       }
+#endif
     }
     // ===== per-cell scalars (cell t4): logsumexp over K, noisy class
     float rs = ((ex[0] + ex[1]) + (ex[2] + ex[3])) + ((ex[4] + ex[5]) + (ex[6] + ex[7]));
