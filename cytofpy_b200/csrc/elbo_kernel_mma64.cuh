@@ -28,6 +28,9 @@ namespace cytof {
 #ifndef CYTOF_X_A2_SKEW
 #define CYTOF_X_A2_SKEW 2   // the log / reciprocal half of a mixture unit runs this many units behind its ex2 half (r2t: cfg5 0.849 -> 0.845 ms, J = 64 0.856 -> 0.837 ms, J = 32 / K = 50 0.660 -> 0.663 ms per 1 M cells)
 #endif
+#ifndef CYTOF_X_MUP_RELOAD
+#define CYTOF_X_MUP_RELOAD 1
+#endif
 #ifndef CYTOF_X_ZPF
 #define CYTOF_X_ZPF 6       // A fragments of Z / Z^T requested this many MMAs ahead (r2y: J=32, K=50, L=5/5 0.6625 -> 0.6485 ms per 1 M cells with 6, 0.6535 with 4; the L=8/8 instances compile to the same code either way)
 #endif
@@ -796,7 +799,24 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   float swdd_l = sq;
 #pragma unroll
   for (int x = 0; x < 2 * NPT; ++x) {
+#if CYTOF_X_MUP_RELOAD
+    // without the imputation path the centred means are only needed here: they are read again (the same expression as
+    // in the prologue, through a load the compiler cannot merge with the first one) instead of holding 2 NPT
+    // registers over the whole loop of a kernel that spills
+    float m = (x & 1) ? hi2(mup[x / 2]) : lo2(mup[x / 2]);
+    if (!MISSING) {
+      const bool z1 = x >= LM0;
+      const int l = z1 ? x - LM0 : x, Lz = z1 ? L1 : L0;
+      m = 0.f;
+      if (l < Lz && x < LM0 + LM1) {
+        float v;
+        asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(G + (z1 ? gl.mu1 : gl.mu0) + l));
+        m = v - (z1 ? mc1 : mc0);
+      }
+    }
+#else
     const float m = (x & 1) ? hi2(mup[x / 2]) : lo2(mup[x / 2]);
+#endif
     const float a = ((x & 1) ? hi2(swm[x / 2]) : lo2(swm[x / 2]));
     const float bm = ((x & 1) ? hi2(swym[x / 2]) : lo2(swym[x / 2]));
     const float at = ((x & 1) ? hi2(swt[x / 2]) : lo2(swt[x / 2]));
