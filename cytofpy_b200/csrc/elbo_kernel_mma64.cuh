@@ -28,6 +28,9 @@ namespace cytof {
 #ifndef CYTOF_X_A2_SKEW
 #define CYTOF_X_A2_SKEW 2   // the log / reciprocal half of a mixture unit runs this many units behind its ex2 half (r2t: cfg5 0.849 -> 0.845 ms, J = 64 0.856 -> 0.837 ms, J = 32 / K = 50 0.660 -> 0.663 ms per 1 M cells)
 #endif
+#ifndef CYTOF_X_SMEMCONST
+#define CYTOF_X_SMEMCONST 1
+#endif
 #ifndef CYTOF_X_MUP_RELOAD
 #define CYTOF_X_MUP_RELOAD 1
 #endif
@@ -51,10 +54,13 @@ constexpr int kXNCJ = 6, kXNCK = 8;       // k-chunks of 8 over markers and over
 // CTA-level region after the Z tables (CYTOF_X_TMEM): header (2 mbarriers, TMEM base) and the operand
 // tiles of the 4 warp PAIRS, double-buffered: A = [D_hi (64 rows) ; D_lo (64 rows)] x 8 cells, B = [g_hi ; g_lo]
 constexpr int kXUFloats = CYTOF_X_TMEM ? 16 + 4 * 2 * 2 * 1024 : 0;
-constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4 + kXUFloats;
+// CTA-level constant tables (CYTOF_X_SMEMCONST, narrow layout): intercepts of the tail markers [8 pairs][32 lanes] float2
+// and log W in accumulator order [8 g][8] -- 24 registers of a kernel that spills at L = 8/8
+constexpr int kXCFloats = 8 * 32 * 2 + 64;
+constexpr int kXZFloats = (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4 + kXUFloats + kXCFloats;
 // WIDE instances (48 < J <= 64, NTP = 4: every cell takes a second full pass over markers 32..63): 64-marker tiles
 constexpr int kXDSW = 68, kXJSW = 64, kXMTJW = 4, kXNCJW = 8;
-constexpr int kXZFloatsW = (kXMTK * kXNCJW + kXMTJW * kXNCK) * 32 * 4 + kXUFloats;
+constexpr int kXZFloatsW = (kXMTK * kXNCJW + kXMTJW * kXNCK) * 32 * 4 + kXUFloats + kXCFloats;
 // c = F32, a = b = TF32, both K-major, N = 128, M = 128
 constexpr uint32_t kUmmaIdesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 // per warp (floats): D hi/lo [2][8][52] | g hi/lo [2][8][68] | A0/c1 [4][52] | y^2 [4][52] |
@@ -148,6 +154,11 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   unsigned char* sU = reinterpret_cast<unsigned char*>(uhdr + 16);                  // [pair][buf][A | B][4096 B]
   unsigned char* myU = sU + (warp >> 1) * (2 * 2 * 4096);                           // this warp pair's tiles
 #endif
+  // only the L > 5 instances spill; for the others the table loads cost more than the registers (J=32, K=50, L=5/5:
+  // 0.650 -> 0.658 ms per 1 M cells with the tables, cfg5 shapes at L=8/8 0.836 -> 0.766)
+  constexpr bool CSM = CYTOF_X_SMEMCONST && !WIDE && NPT > 5;
+  float2* sAlt = reinterpret_cast<float2*>(smem + (kXMTK * kXNCJ + kXMTJ * kXNCK) * 32 * 4 + kXUFloats);   // [8][32]
+  float* sLw = reinterpret_cast<float*>(sAlt + 8 * 32);                                                     // [8 g][8]
   float* wbase = wbase0 + warp * kXWarpFloats;
   float* sDb = wbase;                              // [2][8][kXDS] row 2c = hi(D) of cell c, 2c+1 = lo(D)
   float* sGb = sDb + 2 * 8 * kXDS;                 // [2][8][kXGS] e, then g = fac rho softmax: hi / lo rows
@@ -260,6 +271,14 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   for (int r = 0; r < 8; ++r) {
     const int k = 16 * (r >> 1) + g + 8 * (r & 1);
     lwk[r] = k < K ? G[gl.lw + i * K + k] * kLog2e : kNegBig;
+  }
+  if (CSM && warp == 0) {     // every warp of the CTA holds the same values (same sample, same lane -> marker map)
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) sAlt[q * 32 + lane] = alt[q];
+    if (t4 == 0) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sLw[g * 8 + r] = lwk[r];
+    }
   }
   // imputation parameters of this lane's main marker and tail marker (vae.py:12-13), missingness b
   const int jtl = tail_ok ? jt : 0;
@@ -392,7 +411,7 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
   // the unit, a2 (called one unit later, so the MUFU pipe already works on the next exponentials
   // while these sums settle) takes the logs / reciprocal and writes the tiles of buffer `b`
   struct AState { float S0, S1, B0, B1, yv; };
-  auto phase_a1 = [&](const int un, const float* src, const unsigned mm, const unsigned tm) -> AState {
+  auto phase_a1 = [&](const int un, const float* src, const unsigned mm, const unsigned tm, const bool in_loop = true) -> AState {
     AState st;
     if (un < kXT) {                               // main pass: cell un, marker lane
       const float x = src[un * kXJS + lane];
@@ -402,7 +421,14 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
       const int cu = (un - kXT) * CPT + tcell;
       const float x = tail_ok ? src[cu * kXJS + jt] : 0.f;
       st.yv = (MISSING && ((tm >> (un - kXT)) & 1u)) ? fmaf(sd_t, x, vm_t) : x;
-      mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, alt, ee[un], st.S0, st.S1, st.B0, st.B1);
+      if (CSM && in_loop) {      // the tail intercepts come from the CTA table (one unit per tile uses them)
+        float2 al_t[NPT];
+#pragma unroll
+        for (int q = 0; q < NPT; ++q) al_t[q] = sAlt[q * 32 + lane];
+        mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, al_t, ee[un], st.S0, st.S1, st.B0, st.B1);
+      } else {
+        mix_forward<LM0, NC, NPT>(st.yv, mc0, mc1, nh2, be, alt, ee[un], st.S0, st.S1, st.B0, st.B1);
+      }
     }
     return st;
   };
@@ -498,10 +524,10 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
     __syncwarp();
     if (MISSING) prepass(0, 0, mmask, tmask, amask);
     {
-      AState prev = phase_a1(0, sYb, mmask, tmask);
+      AState prev = phase_a1(0, sYb, mmask, tmask, false);
 #pragma unroll
       for (int un = 1; un < NU; ++un) {
-        const AState now = phase_a1(un, sYb, mmask, tmask);
+        const AState now = phase_a1(un, sYb, mmask, tmask, false);
         phase_a2(un - 1, prev, 0);
         prev = now;
       }
@@ -535,11 +561,19 @@ elbo_fwdbwd_mma64_kernel(const ElboParams p) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) rb[4 * q4 + m] = r4[m];
       }
+      if (CSM) {
+        const float4 l0 = *reinterpret_cast<const float4*>(sLw + g * 8), l1 = *reinterpret_cast<const float4*>(sLw + g * 8 + 4);
+        fT[0][0] = l0.x; fT[0][2] = l0.y; fT[1][0] = l0.z; fT[1][2] = l0.w;
+        fT[2][0] = l1.x; fT[2][2] = l1.y; fT[3][0] = l1.z; fT[3][2] = l1.w;
 #pragma unroll
-      for (int mt = 0; mt < kXMTK; ++mt) {
-        fT[mt][0] = lwk[2 * mt];
-        fT[mt][2] = lwk[2 * mt + 1];
-        fT[mt][1] = fT[mt][3] = 0.f;
+        for (int mt = 0; mt < kXMTK; ++mt) fT[mt][1] = fT[mt][3] = 0.f;
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < kXMTK; ++mt) {
+          fT[mt][0] = lwk[2 * mt];
+          fT[mt][2] = lwk[2 * mt + 1];
+          fT[mt][1] = fT[mt][3] = 0.f;
+        }
       }
 #if CYTOF_X_ZPF > 0 && CYTOF_X_NOGUARD
       {   // the A fragments of Z^T are requested CYTOF_X_ZPF MMAs ahead of their use (each feeds ONE MMA here)
